@@ -1,0 +1,321 @@
+"""Oracle restatement of the torchsparse v1.1.0 operators the reference calls.
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/__init__.py).
+
+torchsparse v1.1.0 (mit-han-lab/torchsparse, tag v1.1.0, pinned by the
+reference at docker/Dockerfile:33) is absent from /root/reference; each function
+below restates its published algorithm and cites
+the reference call site that constrains it.  numpy is used for integer work,
+torch-CPU (fp32, autograd) for feature arithmetic.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+FNV_OFFSET = np.uint64(14695981039346656037)
+FNV_PRIME = np.uint64(1099511628211)
+_MASK60 = np.uint64(0x0FFFFFFFFFFFFFFF)
+
+
+# --------------------------------------------------------------------------- A.1
+def fnv_hash_vec(arr: np.ndarray) -> np.ndarray:
+    """64-bit multiply-then-xor hash over the columns of ``arr`` (App. A.1).
+
+    Used by sparse_quantize at semantic_kitti_dataloader.py:231.
+    """
+    assert arr.ndim == 2
+    a = arr.astype(np.int64).astype(np.uint64)
+    h = np.full(a.shape[0], FNV_OFFSET, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for j in range(a.shape[1]):
+            h = h * FNV_PRIME
+            h = np.bitwise_xor(h, a[:, j])
+    return h
+
+
+def sparse_quantize(coords, feats=None, labels=None, ignore_label=-100,
+                    return_index=False, return_invs=False, hash_type="fnv",
+                    quantization_size=1):
+    """CPU voxel dedup (App. A.1); call site semantic_kitti_dataloader.py:231.
+
+    Returns first-occurrence indices in ascending 64-bit key order, and the
+    inverse map (rank of each point's key).
+    """
+    assert hash_type == "fnv"
+    coords = np.asarray(coords)
+    use_label = labels is not None
+    use_feat = feats is not None
+    if not use_label and not use_feat:
+        return_index = True
+    discrete = np.floor(coords / quantization_size)
+    key = fnv_hash_vec(discrete)
+    if use_label:
+        _, inds, invs, counts = np.unique(key, return_index=True, return_inverse=True,
+                                          return_counts=True)
+        filtered = np.array(labels)[inds]
+        filtered[counts > 1] = ignore_label
+        if return_index:
+            return (inds, filtered, invs) if return_invs else (inds, filtered)
+        out = (discrete[inds], feats[inds], filtered)
+        return out + (invs,) if return_invs else out
+    _, inds, invs = np.unique(key, return_index=True, return_inverse=True)
+    if return_index:
+        return (inds, invs) if return_invs else inds
+    out = (discrete[inds], feats[inds]) if use_feat else (discrete[inds],)
+    out = out + (invs,) if return_invs else out
+    return out if len(out) > 1 else out[0]
+
+
+# --------------------------------------------------------------------------- A.2
+def sphash(coords, offsets=None) -> torch.Tensor:
+    """FNV-1a-64 over the four int32 words (x,y,z,b), folded to 60 bits (App. A.2).
+
+    Call sites: models/utils.py:19,46-52,74-79.  With ``offsets`` [K,3] the
+    result is offset-major [K,N] of hash(x+dx, y+dy, z+dz, b).
+    """
+    c = np.ascontiguousarray(torch.as_tensor(coords).to(torch.int32).numpy())
+    assert c.ndim == 2 and c.shape[1] == 4
+
+    def _h(words):  # words int32 [..., 4]
+        u = words.astype(np.int32).view(np.uint32).astype(np.uint64)
+        h = np.full(u.shape[:-1], FNV_OFFSET, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            for j in range(4):
+                h = np.bitwise_xor(h, u[..., j])
+                h = h * FNV_PRIME
+        h = np.bitwise_xor(h >> np.uint64(60), h & _MASK60)
+        return h.astype(np.int64)
+
+    if offsets is None:
+        return torch.from_numpy(_h(c))
+    off = np.ascontiguousarray(torch.as_tensor(offsets).to(torch.int32).numpy())
+    K = off.shape[0]
+    with np.errstate(over="ignore"):
+        shifted = np.repeat(c[None, :, :], K, axis=0).copy()
+        shifted[:, :, :3] = (shifted[:, :, :3].astype(np.int64) + off[:, None, :].astype(np.int64)).astype(np.int32)
+    return torch.from_numpy(_h(shifted))
+
+
+# --------------------------------------------------------------------------- A.3
+def sphashquery(queries: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """Index of each query key in ``targets`` or -1 (App. A.3; utils.py:21,50,80)."""
+    q = queries.to(torch.int64).numpy()
+    t = targets.to(torch.int64).numpy().reshape(-1)
+    shape = q.shape
+    q = q.reshape(-1)
+    if t.size == 0:
+        return torch.full(shape, -1, dtype=torch.int64)
+    order = np.argsort(t, kind="stable")
+    ts = t[order]
+    pos = np.searchsorted(ts, q, side="left")
+    pos_c = np.minimum(pos, ts.size - 1)
+    hit = ts[pos_c] == q
+    out = np.where(hit, order[pos_c], -1).astype(np.int64)
+    return torch.from_numpy(out.reshape(shape))
+
+
+# --------------------------------------------------------------------------- A.4
+def spcount(idx: torch.Tensor, num: int) -> torch.Tensor:
+    """Histogram of idx>=0 into ``num`` bins, int32 (utils.py:22,51)."""
+    i = idx.to(torch.int64)
+    i = i[i >= 0]
+    return torch.bincount(i, minlength=num).to(torch.int32)
+
+
+def spvoxelize(feat: torch.Tensor, idx: torch.Tensor, cnt: torch.Tensor) -> torch.Tensor:
+    """out[idx[i]] += feat[i] / cnt[idx[i]] (utils.py:24,27,58); autograd via torch."""
+    i = idx.to(torch.int64)
+    valid = i >= 0
+    iv = i[valid]
+    scaled = feat[valid] / cnt.to(feat.dtype)[iv].unsqueeze(1)
+    out = torch.zeros(cnt.shape[0], feat.shape[1], dtype=feat.dtype)
+    return out.index_add(0, iv, scaled)
+
+
+def spdevoxelize(feat: torch.Tensor, idx: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """out[i] = sum_k w[i,k] * feat[idx[i,k]] over idx>=0 (utils.py:87,99)."""
+    i = idx.to(torch.int64)
+    valid = (i >= 0)
+    g = feat[i.clamp(min=0)]                       # [N,8,C]
+    wv = (w * valid.to(w.dtype)).unsqueeze(-1)
+    return (g * wv).sum(1)
+
+
+def calc_ti_weights(pc: torch.Tensor, idx_query: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """Trilinear weights [8,N] in KernelRegion(2) order (App. A.4; utils.py:81)."""
+    with torch.no_grad():
+        p = pc[:, :3]
+        fl = torch.floor(p / scale) * scale if scale != 1 else torch.floor(p)
+        ce = fl + scale
+        lo = p - fl        # (x - flx)
+        hi = ce - p        # (cex - x)
+        ws = []
+        for bx in (0, 1):
+            for by in (0, 1):
+                for bz in (0, 1):
+                    fx = lo[:, 0] if bx else hi[:, 0]
+                    fy = lo[:, 1] if by else hi[:, 1]
+                    fz = lo[:, 2] if bz else hi[:, 2]
+                    ws.append(fx * fy * fz)
+        w = torch.stack(ws, 0)
+        if scale != 1:
+            w = w / (scale ** 3)
+        w[idx_query == -1] = 0
+        w = w / (w.sum(0) + 1e-8)
+    return w
+
+
+# --------------------------------------------------------------------------- A.5
+class KernelRegion:
+    """Kernel offsets (App. A.5): odd ks ordered z-outer/x-inner, even ks x-outer/z-inner."""
+
+    def __init__(self, kernel_size=3, tensor_stride=1, dilation=1):
+        self.kernel_size, self.tensor_stride, self.dilation = kernel_size, tensor_stride, dilation
+        ks = kernel_size
+        axis = [v * tensor_stride * dilation for v in range(-ks // 2 + 1, ks // 2 + 1)]
+        if ks % 2 == 1:
+            offs = [[x, y, z] for z in axis for y in axis for x in axis]
+        else:
+            offs = [[x, y, z] for x in axis for y in axis for z in axis]
+        self.kernel_offset = np.array(offs, dtype=np.int32)
+
+    def get_kernel_offset(self) -> torch.Tensor:
+        return torch.from_numpy(self.kernel_offset.copy())
+
+
+# --------------------------------------------------------------------------- A.6
+def convert_neighbor_map(nbr: torch.Tensor):
+    """[K,M] neighbour table -> (pairs [L,2] int32 (in,out) k-major/out-ascending, counts [K])."""
+    n = nbr.numpy()
+    k_idx, j_idx = np.nonzero(n != -1)
+    pairs = np.stack([n[k_idx, j_idx], j_idx], 1).astype(np.int32)
+    counts = (n != -1).sum(1).astype(np.int32)
+    return torch.from_numpy(pairs), torch.from_numpy(counts)
+
+
+def spdownsample(coords: torch.Tensor, ratio: int) -> torch.Tensor:
+    """Coarser coordinates in ascending-hash order (App. A.6 `spdownsample`)."""
+    cf = coords[:, :3].float()
+    cn = torch.floor(torch.floor(cf / ratio) * ratio).int()
+    cn = torch.cat([cn, coords[:, 3].view(-1, 1).int()], 1)
+    h = sphash(cn)
+    _, inv, cnt = torch.unique(h, return_inverse=True, return_counts=True)
+    uq = torch.round(spvoxelize(cn.float(), inv.int(), cnt.int()))
+    return uq.int()
+
+
+def build_kernel_map(coords_in: torch.Tensor, coords_out: torch.Tensor, kernel_size: int,
+                     cur_stride: int):
+    """Neighbour table [K,N_out] + reference-format pair list (App. A.6)."""
+    off = KernelRegion(kernel_size, cur_stride).get_kernel_offset()
+    nbr = sphashquery(sphash(coords_out, off), sphash(coords_in))
+    pairs, counts = convert_neighbor_map(nbr)
+    return nbr, pairs, counts
+
+
+def sparseconv(feats: torch.Tensor, kernel: torch.Tensor, pairs: torch.Tensor, counts: torch.Tensor,
+               sizes, transpose: bool) -> torch.Tensor:
+    """Offset-by-offset gather -> mm -> scatter-add (App. A.6 arithmetic), autograd via torch."""
+    n_out = sizes[0] if transpose else sizes[1]
+    out = torch.zeros(n_out, kernel.shape[-1], dtype=feats.dtype)
+    p = pairs.to(torch.int64)
+    cur = 0
+    for k in range(kernel.shape[0]):
+        n = int(counts[k])
+        if n == 0:
+            continue
+        seg = p[cur:cur + n]
+        i_in, i_out = (seg[:, 1], seg[:, 0]) if transpose else (seg[:, 0], seg[:, 1])
+        out = out.index_add(0, i_out, feats[i_in] @ kernel[k])
+        cur += n
+    return out
+
+
+class SparseTensor:
+    """Container mirroring torchsparse.SparseTensor (App. A.7; collate.py:67)."""
+
+    def __init__(self, feats, coords, stride=1):
+        self.F, self.C, self.s = feats, coords, stride
+        self.coord_maps, self.kernel_maps = {}, {}
+
+    def check(self):
+        if self.s not in self.coord_maps:
+            self.coord_maps[self.s] = self.C
+
+    def __add__(self, other):
+        t = SparseTensor(self.F + other.F, self.C, self.s)
+        t.coord_maps, t.kernel_maps = self.coord_maps, self.kernel_maps
+        return t
+
+
+class PointTensor:
+    """Container mirroring torchsparse.PointTensor (spvcnn.py:193)."""
+
+    def __init__(self, feat, coords, idx_query=None, weights=None):
+        self.F, self.C = feat, coords
+        self.idx_query = idx_query if idx_query is not None else {}
+        self.weights = weights if weights is not None else {}
+        self.additional_features = {"idx_query": {}, "counts": {}}
+
+
+def cat(tensors):
+    t = SparseTensor(torch.cat([x.F for x in tensors], 1), tensors[0].C, tensors[0].s)
+    t.coord_maps, t.kernel_maps = tensors[0].coord_maps, tensors[0].kernel_maps
+    return t
+
+
+def conv3d(inputs: SparseTensor, kernel: torch.Tensor, kernel_size: int, bias=None, stride=1,
+           dilation=1, transpose=False) -> SparseTensor:
+    """torchsparse.nn.functional.conv3d (App. A.6); all 49 call sites in spvcnn.py."""
+    F, C, s = inputs.F, inputs.C, inputs.s
+    if kernel_size == 1 and stride == 1 and dilation == 1:
+        out = SparseTensor(F.matmul(kernel), C, s)
+        out.coord_maps, out.kernel_maps = inputs.coord_maps, inputs.kernel_maps
+        out.check()
+        return out
+    if not transpose:
+        key = "k%s_os%d_s%d_d%d" % (kernel_size, s, stride, dilation)
+        if stride > 1:
+            new_c = spdownsample(C, stride * s)
+            _, pairs, counts = build_kernel_map(C, new_c, kernel_size, s)
+            sizes = (F.shape[0], new_c.shape[0])
+            out = SparseTensor(sparseconv(F, kernel, pairs, counts, sizes, False), new_c, s * stride)
+            out.coord_maps = dict(inputs.coord_maps)
+            out.check()
+            out.kernel_maps = dict(inputs.kernel_maps)
+            out.kernel_maps[key] = [pairs, counts, sizes]
+        else:
+            km = inputs.kernel_maps.get(key)
+            if km is None:
+                _, pairs, counts = build_kernel_map(C, C, kernel_size, s)
+                km = [pairs, counts, (F.shape[0], F.shape[0])]
+                kernel_maps = dict(inputs.kernel_maps)
+                kernel_maps[key] = km
+            else:
+                kernel_maps = inputs.kernel_maps
+            out = SparseTensor(sparseconv(F, kernel, km[0], km[1], km[2], False), C, s)
+            out.coord_maps = inputs.coord_maps
+            out.check()
+            out.kernel_maps = kernel_maps
+    else:
+        orig = int(s / stride)
+        km = inputs.kernel_maps["k%s_os%d_s%d_d%d" % (kernel_size, orig, stride, dilation)]
+        out = SparseTensor(sparseconv(F, kernel, km[0], km[1], km[2], True),
+                           inputs.coord_maps[orig], orig)
+        out.coord_maps, out.kernel_maps = inputs.coord_maps, inputs.kernel_maps
+        out.check()
+    if bias is not None:
+        out.F = out.F + bias
+    return out
+
+
+def conv_weight_init(kernel: torch.Tensor, in_channels: int, out_channels: int, k: int,
+                     transpose: bool, generator=None):
+    """U(-a,a), a = 1/sqrt(Cout if transposed else Cin*K) (App. A.7)."""
+    std = 1.0 / math.sqrt(out_channels if transpose else in_channels * k)
+    with torch.no_grad():
+        kernel.uniform_(-std, std, generator=generator)
+    return kernel
