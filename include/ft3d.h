@@ -1,0 +1,174 @@
+/* libft3d -- C ABI of the B200-native 3D-branch hot path of FusionTransformer.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + the caller's CUDA
+ * stream, never allocates or frees device memory, never synchronises the host (except where
+ * stated) and returns 0 on success.  On failure it returns a non-zero code and
+ * ft3d_last_error() holds a thread-local message.  All work is enqueued on `stream`.
+ *
+ * The reference (aliabdelkader/FusionTransformer) reaches this arithmetic through the
+ * torchsparse v1.1.0 Python API (docker/Dockerfile:33); each function names the reference
+ * call site (file:line under /root/reference/FusionTransformer) it serves and the upstream
+ * operator it replaces.
+ */
+#ifndef FT3D_H_
+#define FT3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ft3d_stream_t; /* cudaStream_t */
+
+#define FT3D_VERSION 100
+#define FT3D_KPAD_K3 32 /* row pitch (int32) of a 27-offset neighbour table */
+#define FT3D_KPAD_K2 8  /* row pitch (int32) of an 8-offset neighbour table  */
+
+int ft3d_version(void);
+const char* ft3d_last_error(void);
+
+/* ---- K1/K2  spf.sphash  (models/utils.py:19,46-52,74-79) --------------------------------- */
+/* out[i] = fold60(FNV1a64(x,y,z,b)) for coords int32 [n,4]. */
+int ft3d_hash(const int32_t* coords, int64_t n, int64_t* out, ft3d_stream_t stream);
+/* out[k*n+i] = hash(x+dx_k, y+dy_k, z+dz_k, b); offsets int32 [K,3]. */
+int ft3d_kernel_hash(const int32_t* coords, int64_t n, const int32_t* offsets, int32_t K,
+                     int64_t* out, ft3d_stream_t stream);
+
+/* ---- a1  augment_and_scale_3d + cast + bounds (data/utils/augmentation_3d.py:43-46,
+ *          data/semantic_kitti/semantic_kitti_dataloader.py:220,225), no augmentation -------- */
+/* points f32 [n,3]; scan_id int32 [n] in [0,num_scans); min_ws f32 [num_scans*3] scratch.
+ * coords_out int32 [n,4] = (trunc(p*scale - min_scan(p*scale)), scan); keep_out[i] = all in [0,full_scale). */
+int ft3d_scale_coords(const float* points, const int32_t* scan_id, int64_t n, int32_t num_scans,
+                      float scale, int32_t full_scale, int32_t* coords_out, uint8_t* keep_out,
+                      float* min_ws, ft3d_stream_t stream);
+
+/* ---- a2 / K15  torchsparse.utils.sparse_quantize (semantic_kitti_dataloader.py:231) ------- */
+/* coords int32 [n,4] (x,y,z,scan), scans contiguous and ascending.  Per scan: unique 64-bit
+ * FNV-1 keys in ascending order.  inds_out[g] (g < *num_unique_out) = global row of the first
+ * occurrence of unique voxel g (groups ordered by scan, then key); inverse_out[i] = rank of
+ * row i's voxel inside its scan; scan_counts_out[s] = unique voxels of scan s. */
+size_t ft3d_quantize_workspace(int64_t n, int32_t num_scans);
+int ft3d_quantize(const int32_t* coords, int64_t n, int32_t num_scans, int32_t* inds_out,
+                  int32_t* inverse_out, int32_t* scan_counts_out, int32_t* num_unique_out,
+                  void* workspace, size_t workspace_bytes, ft3d_stream_t stream);
+
+/* ---- K4  torch.unique(sorted, return_inverse, return_counts) on hashes
+ *          (models/utils.py:20; torchsparse spdownsample) ----------------------------------- */
+/* uniq_out/counts_out/first_out hold *num_out valid entries; first_out = smallest row index of
+ * each group (stable). */
+size_t ft3d_unique_workspace(int64_t n);
+int ft3d_unique(const int64_t* keys, int64_t n, int64_t* uniq_out, int32_t* inverse_out,
+                int32_t* counts_out, int32_t* first_out, int32_t* num_out, void* workspace,
+                size_t workspace_bytes, ft3d_stream_t stream);
+/* coarse_out[i] = (floor(x/ratio)*ratio, ..., b); hash_out[i] = ft3d_hash(coarse_out[i]). */
+int ft3d_coarsen_hash(const int32_t* coords, int64_t n, int32_t ratio, int32_t* coarse_out,
+                      int64_t* hash_out, ft3d_stream_t stream);
+/* out[g] = src[first[g]] for rows of `width` int32. */
+int ft3d_gather_rows_i32(const int32_t* src, const int32_t* first, int64_t m, int32_t width,
+                         int32_t* out, ft3d_stream_t stream);
+
+/* ---- K3  spf.sphashquery (models/utils.py:21,50,80; torchsparse conv3d) -------------------- */
+/* Open-addressing table owned by the caller: table_keys uint64 [cap], table_vals int32 [cap],
+ * cap = ft3d_table_capacity(n) (power of two).  Key -> row index; duplicate keys keep the
+ * smallest index.  The key value 0xFFFF...F is reserved. */
+int64_t ft3d_table_capacity(int64_t n);
+int ft3d_table_build(const int64_t* keys, int64_t n, uint64_t* table_keys, int32_t* table_vals,
+                     int64_t cap, ft3d_stream_t stream);
+int ft3d_table_query(const int64_t* queries, int64_t m, const uint64_t* table_keys,
+                     const int32_t* table_vals, int64_t cap, int64_t* out, ft3d_stream_t stream);
+
+/* ---- a6/a7/K9  kernel maps (torchsparse conv3d map build, triggered at models/spvcnn.py:99,
+ *               105-124) ---------------------------------------------------------------------- */
+/* nbr_out[j*kpad+k] = row in the table's coordinate set of (coords_q[j] + offsets[k]) or -1;
+ * columns K..kpad-1 = -1.  The table must have been built from ft3d_hash of the input coords. */
+int ft3d_kmap_build(const int32_t* coords_q, int64_t n_out, const int32_t* offsets, int32_t K,
+                    const uint64_t* table_keys, const int32_t* table_vals, int64_t cap,
+                    int32_t* nbr_out, int32_t kpad, ft3d_stream_t stream);
+/* Reference-format map (torchsparse convert_neighbor_map_gpu): pairs_out int32 [L,2] =
+ * (in,out), offset-major then out-ascending; offsets_out int32 [K+1] exclusive prefix of the
+ * per-offset counts (offsets_out[K] = L).  pairs_out must hold K*n_out rows. */
+size_t ft3d_kmap_pairs_workspace(int64_t n_out, int32_t kpad);
+int ft3d_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad,
+                    int32_t* pairs_out, int32_t* offsets_out, void* workspace,
+                    size_t workspace_bytes, ft3d_stream_t stream);
+/* nbrT_out[i*kpad+k] = j where nbr[j*kpad+k] == i, else -1 (input-stationary view for dgrad and
+ * transposed conv, models/spvcnn.py:38-50). */
+int ft3d_kmap_transpose(const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad,
+                        int32_t* nbrT_out, int64_t n_in, ft3d_stream_t stream);
+
+/* ---- K5-K8  point<->voxel (models/utils.py:22-27,51-58,81-99) ------------------------------ */
+int ft3d_count(const int32_t* idx, int64_t n, int32_t* cnt_out, int64_t m, ft3d_stream_t stream);
+int ft3d_voxelize_fwd(const float* feat, const int32_t* idx, const int32_t* cnt, int64_t n,
+                      int64_t m, int32_t c, float* out, ft3d_stream_t stream);
+int ft3d_voxelize_bwd(const float* gout, const int32_t* idx, const int32_t* cnt, int64_t n,
+                      int64_t m, int32_t c, float* gin, ft3d_stream_t stream);
+int ft3d_devoxelize_fwd(const float* feat, const int32_t* idx, const float* w, int64_t n,
+                        int64_t m, int32_t c, float* out, ft3d_stream_t stream);
+int ft3d_devoxelize_bwd(const float* gout, const int32_t* idx, const float* w, int64_t n,
+                        int64_t m, int32_t c, float* gfeat, ft3d_stream_t stream);
+/* spf.calc_ti_weights: pc f32 [n,4], idx int64 [8,n] -> w_out f32 [8,n]. */
+int ft3d_ti_weights(const float* pc, const int64_t* idx, int64_t n, float scale, float* w_out,
+                    ft3d_stream_t stream);
+/* Fused voxel_to_point map build (models/utils.py:71-85): for each point the 8 corner voxels of
+ * its stride-`stride` cell looked up in the table, plus normalised trilinear weights.
+ * idx_out int32 [n,8], w_out f32 [n,8]. */
+int ft3d_v2p_build(const float* pc, int64_t n, int32_t stride, const uint64_t* table_keys,
+                   const int32_t* table_vals, int64_t cap, int32_t* idx_out, float* w_out,
+                   ft3d_stream_t stream);
+/* Fused point_to_voxel map build (models/utils.py:46-53): idx_out[i] = voxel row of
+ * floor(pc[i]/stride)*stride or -1; cnt_out int32 [m] = points per voxel. */
+int ft3d_p2v_build(const float* pc, int64_t n, int32_t stride, const uint64_t* table_keys,
+                   const int32_t* table_vals, int64_t cap, int32_t* idx_out, int32_t* cnt_out,
+                   int64_t m, ft3d_stream_t stream);
+
+/* ---- a15/K16  2D->3D lift (models/image_models_billinear.py:117-124) ----------------------- */
+/* out[p,c] = fmap[b(p), c, row(p), col(p)]; fmap addressed by element strides (sb,sc,sh,sw) so
+ * both NCHW and channels-last maps work; rc int32 [n,2] = (row,col); bidx int32 [n]. */
+int ft3d_lift_fwd(const float* fmap, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t B,
+                  int32_t C, int32_t H, int32_t W, const int32_t* rc, const int32_t* bidx,
+                  int64_t n, float* out, ft3d_stream_t stream);
+/* gmap (same strides) += scatter of gout; the caller zero-fills gmap. */
+int ft3d_lift_bwd(const float* gout, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t B,
+                  int32_t C, int32_t H, int32_t W, const int32_t* rc, const int32_t* bidx,
+                  int64_t n, float* gmap, ft3d_stream_t stream);
+
+/* ---- a8-a10/K11-K13  sparse convolution (all 49 spnn.Conv3d of models/spvcnn.py) ----------- */
+/* Output-stationary gather-GEMM:  out[j,:] = sum_k  in[nbr[j,k],:] @ B_k   (rows with nbr<0 skipped)
+ *   forward    : in = features,   nbr = map,             B_k = W[k]            (red=Cin,  n=Cout)
+ *   dgrad      : in = grad_out,   nbr = transposed map,  B_k = W[k]^T          (red=Cout, n=Cin)
+ *   k3 stride-1 dgrad reuses the forward table with kflip=1 (nbrT[i,k] == nbr[i,K-1-k]).
+ * fp32 CUDA-core variant (exact-precision mode): w f32 [K,Cin,Cout]; w_transposed=1 uses W[k]^T. */
+int ft3d_conv_gather_f32(const float* in, const int32_t* nbr, int64_t n_out, int32_t K,
+                         int32_t kpad, int32_t kflip, int32_t red, int32_t ncols, const float* w,
+                         int32_t w_transposed, float* out, ft3d_stream_t stream);
+/* bf16 tcgen05 variant: operands rounded to bf16, fp32 accumulation in TMEM.  `wpacked` is the
+ * image written by ft3d_conv_pack_weights for the same (K, red, ncols, w_transposed). */
+size_t ft3d_conv_packed_bytes(int32_t K, int32_t red, int32_t ncols);
+int ft3d_conv_pack_weights(const float* w, int32_t K, int32_t cin, int32_t cout,
+                           int32_t w_transposed, void* wpacked, ft3d_stream_t stream);
+int ft3d_conv_gather_tc(const float* in, const int32_t* nbr, int64_t n_out, int32_t K,
+                        int32_t kpad, int32_t kflip, int32_t red, int32_t ncols,
+                        const void* wpacked, float* out, ft3d_stream_t stream);
+/* wgrad: gw[k] += sum over pairs p of offset k of  a[pairs[p,ca],:]^T  b[pairs[p,cb],:]
+ *   forward conv : a = features [.,cin], ca = 0 ; b = grad_out [.,cout], cb = 1
+ *   transposed   : ca = 1, cb = 0 (pair columns swapped, models/spvcnn.py:42-46)
+ * pair_offsets int32 [K+1] on device; max_pairs = host-side upper bound on L used to size the grid.
+ * gw f32 [K,cin,cout] is accumulated into (caller zero-fills). */
+int ft3d_conv_wgrad_f32(const float* a, const float* b, const int32_t* pairs,
+                        const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
+                        int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
+int ft3d_conv_wgrad_tc(const float* a, const float* b, const int32_t* pairs,
+                       const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
+                       int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
+
+/* ---- self-test of the tcgen05 building block (tests only): D[128,n] = A[128,kdim] B[n,kdim]^T
+ * with bf16 operands in the layouts the conv kernels use.  mode 0 = K-major, 1 = MN-major. */
+int ft3d_umma_selftest(const float* a, const float* b, int32_t n, int32_t kdim, int32_t mode,
+                       float* d, ft3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FT3D_H_ */
