@@ -1,0 +1,358 @@
+"""Thin torch-tensor wrappers over the libft3d C ABI (include/ft3d.h).
+
+PyTorch is used only for device memory (caching allocator) and the current stream; every wrapper
+hands raw device pointers, sizes and the stream to one C entry point.  No wrapper has a CPU or
+PyTorch fallback: a non-CUDA tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import Ft3dError, lib
+
+KPAD = {27: 32, 8: 8}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise Ft3dError("%s must be a CUDA tensor: libft3d has no CPU fallback" % name)
+    if t.dtype != dtype:
+        raise Ft3dError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------- hashing / tables
+def hash_coords(coords: torch.Tensor) -> torch.Tensor:
+    coords = _chk(coords, torch.int32, "coords")
+    n = coords.shape[0]
+    out = torch.empty(n, dtype=torch.int64, device=coords.device)
+    lib().hash(coords.data_ptr(), n, out.data_ptr(), _stream())
+    return out
+
+
+def kernel_hash(coords: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    coords = _chk(coords, torch.int32, "coords")
+    offsets = _chk(offsets, torch.int32, "offsets")
+    n, k = coords.shape[0], offsets.shape[0]
+    out = torch.empty((k, n), dtype=torch.int64, device=coords.device)
+    lib().kernel_hash(coords.data_ptr(), n, offsets.data_ptr(), k, out.data_ptr(), _stream())
+    return out
+
+
+class CoordTable:
+    """Open-addressing table hash(coord) -> row; built once per coordinate set and reused by every
+    map that looks voxels up in it (kernel maps, point->voxel, voxel->point)."""
+
+    __slots__ = ("keys", "vals", "cap", "n")
+
+    def __init__(self, hashes: torch.Tensor):
+        hashes = _chk(hashes, torch.int64, "hashes")
+        self.n = hashes.numel()
+        self.cap = int(lib().table_capacity(self.n))
+        self.keys = torch.empty(self.cap, dtype=torch.int64, device=hashes.device)
+        self.vals = torch.empty(self.cap, dtype=torch.int32, device=hashes.device)
+        lib().table_build(hashes.data_ptr(), self.n, self.keys.data_ptr(), self.vals.data_ptr(), self.cap, _stream())
+
+    @classmethod
+    def from_coords(cls, coords: torch.Tensor) -> "CoordTable":
+        return cls(hash_coords(coords))
+
+    def query(self, queries: torch.Tensor) -> torch.Tensor:
+        q = _chk(queries, torch.int64, "queries")
+        out = torch.empty_like(q)
+        lib().table_query(q.data_ptr(), q.numel(), self.keys.data_ptr(), self.vals.data_ptr(), self.cap,
+                          out.data_ptr(), _stream())
+        return out
+
+
+# ----------------------------------------------------------------------------- unique / quantize
+def unique_sorted(keys: torch.Tensor):
+    """(unique ascending, inverse int32, counts int32, first-occurrence row int32) of int64 keys."""
+    keys = _chk(keys, torch.int64, "keys")
+    n = keys.numel()
+    dev = keys.device
+    uniq = torch.empty(n, dtype=torch.int64, device=dev)
+    inverse = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    first = torch.empty(n, dtype=torch.int32, device=dev)
+    num = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = lib().unique_workspace(n)
+    ws = _ws(wsb, dev)
+    lib().unique(keys.data_ptr(), n, uniq.data_ptr(), inverse.data_ptr(), counts.data_ptr(), first.data_ptr(),
+                 num.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    m = int(num.item())            # one host read per coordinate level (sizes the next allocation)
+    return uniq[:m], inverse, counts[:m], first[:m]
+
+
+def scale_coords(points: torch.Tensor, scan_id: torch.Tensor, num_scans: int, scale: float, full_scale: int):
+    points = _chk(points, torch.float32, "points")
+    scan_id = _chk(scan_id, torch.int32, "scan_id")
+    n = points.shape[0]
+    dev = points.device
+    coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    mins = torch.empty(num_scans * 3, dtype=torch.float32, device=dev)
+    lib().scale_coords(points.data_ptr(), scan_id.data_ptr(), n, num_scans, float(scale), int(full_scale),
+                       coords.data_ptr(), keep.data_ptr(), mins.data_ptr(), _stream())
+    return coords, keep.bool()
+
+
+def quantize(coords: torch.Tensor, num_scans: int):
+    """GPU sparse_quantize over a batch of scans: (inds int32 [U], inverse int32 [n], per-scan unique counts)."""
+    coords = _chk(coords, torch.int32, "coords")
+    n = coords.shape[0]
+    dev = coords.device
+    inds = torch.empty(n, dtype=torch.int32, device=dev)
+    inverse = torch.empty(n, dtype=torch.int32, device=dev)
+    scan_counts = torch.empty(num_scans, dtype=torch.int32, device=dev)
+    num = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(lib().quantize_workspace(n, num_scans), dev)
+    lib().quantize(coords.data_ptr(), n, num_scans, inds.data_ptr(), inverse.data_ptr(), scan_counts.data_ptr(),
+                   num.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    u = int(num.item())
+    return inds[:u], inverse, scan_counts
+
+
+def coarsen_hash(coords: torch.Tensor, ratio: int):
+    coords = _chk(coords, torch.int32, "coords")
+    n = coords.shape[0]
+    coarse = torch.empty_like(coords)
+    h = torch.empty(n, dtype=torch.int64, device=coords.device)
+    lib().coarsen_hash(coords.data_ptr(), n, int(ratio), coarse.data_ptr(), h.data_ptr(), _stream())
+    return coarse, h
+
+
+def gather_rows_i32(src: torch.Tensor, first: torch.Tensor) -> torch.Tensor:
+    src = _chk(src, torch.int32, "src")
+    first = _chk(first, torch.int32, "first")
+    m, w = first.numel(), src.shape[1]
+    out = torch.empty((m, w), dtype=torch.int32, device=src.device)
+    lib().gather_rows_i32(src.data_ptr(), first.data_ptr(), m, w, out.data_ptr(), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- kernel maps
+def kmap_build(coords_q: torch.Tensor, offsets: torch.Tensor, table: CoordTable) -> torch.Tensor:
+    coords_q = _chk(coords_q, torch.int32, "coords_q")
+    offsets = _chk(offsets, torch.int32, "offsets")
+    k = offsets.shape[0]
+    kpad = KPAD[k]
+    n_out = coords_q.shape[0]
+    nbr = torch.empty((n_out, kpad), dtype=torch.int32, device=coords_q.device)
+    lib().kmap_build(coords_q.data_ptr(), n_out, offsets.data_ptr(), k, table.keys.data_ptr(),
+                     table.vals.data_ptr(), table.cap, nbr.data_ptr(), kpad, _stream())
+    return nbr
+
+
+def kmap_pairs(nbr: torch.Tensor, k: int):
+    """Reference-format pair list (upper-bound sized) and device-side prefix offsets [K+1]."""
+    nbr = _chk(nbr, torch.int32, "nbr")
+    n_out, kpad = nbr.shape
+    dev = nbr.device
+    pairs = torch.empty((max(n_out * k, 1), 2), dtype=torch.int32, device=dev)
+    offsets = torch.empty(k + 1, dtype=torch.int32, device=dev)
+    ws = _ws(lib().kmap_pairs_workspace(n_out, kpad), dev)
+    lib().kmap_pairs(nbr.data_ptr(), n_out, k, kpad, pairs.data_ptr(), offsets.data_ptr(), ws.data_ptr(),
+                     ws.numel(), _stream())
+    return pairs, offsets
+
+
+def kmap_transpose(nbr: torch.Tensor, k: int, n_in: int) -> torch.Tensor:
+    nbr = _chk(nbr, torch.int32, "nbr")
+    n_out, kpad = nbr.shape
+    out = torch.empty((n_in, kpad), dtype=torch.int32, device=nbr.device)
+    lib().kmap_transpose(nbr.data_ptr(), n_out, k, kpad, out.data_ptr(), n_in, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- point <-> voxel
+def count(idx: torch.Tensor, m: int) -> torch.Tensor:
+    idx = _chk(idx, torch.int32, "idx")
+    out = torch.empty(m, dtype=torch.int32, device=idx.device)
+    lib().count(idx.data_ptr(), idx.numel(), out.data_ptr(), m, _stream())
+    return out
+
+
+def voxelize_fwd(feat, idx, cnt):
+    feat = _chk(feat, torch.float32, "feat")
+    idx = _chk(idx, torch.int32, "idx")
+    cnt = _chk(cnt, torch.int32, "cnt")
+    n, c = feat.shape
+    m = cnt.numel()
+    out = torch.empty((m, c), dtype=torch.float32, device=feat.device)
+    lib().voxelize_fwd(feat.data_ptr(), idx.data_ptr(), cnt.data_ptr(), n, m, c, out.data_ptr(), _stream())
+    return out
+
+
+def voxelize_bwd(gout, idx, cnt, n):
+    gout = _chk(gout, torch.float32, "gout")
+    m, c = gout.shape
+    gin = torch.empty((n, c), dtype=torch.float32, device=gout.device)
+    lib().voxelize_bwd(gout.data_ptr(), idx.data_ptr(), cnt.data_ptr(), n, m, c, gin.data_ptr(), _stream())
+    return gin
+
+
+def devoxelize_fwd(feat, idx, w):
+    feat = _chk(feat, torch.float32, "feat")
+    idx = _chk(idx, torch.int32, "idx")
+    w = _chk(w, torch.float32, "w")
+    m, c = feat.shape
+    n = idx.shape[0]
+    out = torch.empty((n, c), dtype=torch.float32, device=feat.device)
+    lib().devoxelize_fwd(feat.data_ptr(), idx.data_ptr(), w.data_ptr(), n, m, c, out.data_ptr(), _stream())
+    return out
+
+
+def devoxelize_bwd(gout, idx, w, m):
+    gout = _chk(gout, torch.float32, "gout")
+    n, c = gout.shape
+    gfeat = torch.empty((m, c), dtype=torch.float32, device=gout.device)
+    lib().devoxelize_bwd(gout.data_ptr(), idx.data_ptr(), w.data_ptr(), n, m, c, gfeat.data_ptr(), _stream())
+    return gfeat
+
+
+def ti_weights(pc, idx_query, scale):
+    pc = _chk(pc, torch.float32, "pc")
+    idx_query = _chk(idx_query, torch.int64, "idx_query")
+    if pc.shape[1] != 4:
+        raise Ft3dError("calc_ti_weights expects point coordinates [N,4]")
+    n = pc.shape[0]
+    w = torch.empty((8, n), dtype=torch.float32, device=pc.device)
+    lib().ti_weights(pc.data_ptr(), idx_query.data_ptr(), n, float(scale), w.data_ptr(), _stream())
+    return w
+
+
+def v2p_build(pc, stride, table: CoordTable):
+    pc = _chk(pc, torch.float32, "pc")
+    n = pc.shape[0]
+    idx = torch.empty((n, 8), dtype=torch.int32, device=pc.device)
+    w = torch.empty((n, 8), dtype=torch.float32, device=pc.device)
+    lib().v2p_build(pc.data_ptr(), n, int(stride), table.keys.data_ptr(), table.vals.data_ptr(), table.cap,
+                    idx.data_ptr(), w.data_ptr(), _stream())
+    return idx, w
+
+
+def p2v_build(pc, stride, table: CoordTable, m):
+    pc = _chk(pc, torch.float32, "pc")
+    n = pc.shape[0]
+    idx = torch.empty(n, dtype=torch.int32, device=pc.device)
+    cnt = torch.empty(m, dtype=torch.int32, device=pc.device)
+    lib().p2v_build(pc.data_ptr(), n, int(stride), table.keys.data_ptr(), table.vals.data_ptr(), table.cap,
+                    idx.data_ptr(), cnt.data_ptr(), m, _stream())
+    return idx, cnt
+
+
+# ----------------------------------------------------------------------------- lift
+def _fmap_strides(fmap):
+    if fmap.dim() != 4:
+        raise Ft3dError("feature map must be [B,C,H,W]")
+    return fmap.stride(0), fmap.stride(1), fmap.stride(2), fmap.stride(3)
+
+
+def lift_fwd(fmap, rc, bidx):
+    if not (fmap.is_cuda and fmap.dtype == torch.float32):
+        raise Ft3dError("feature map must be a CUDA float32 tensor")
+    rc = _chk(rc, torch.int32, "rc")
+    bidx = _chk(bidx, torch.int32, "bidx")
+    b, c, h, w = fmap.shape
+    sb, sc, sh, sw = _fmap_strides(fmap)
+    n = rc.shape[0]
+    out = torch.empty((n, c), dtype=torch.float32, device=fmap.device)
+    lib().lift_fwd(fmap.data_ptr(), sb, sc, sh, sw, b, c, h, w, rc.data_ptr(), bidx.data_ptr(), n, out.data_ptr(),
+                   _stream())
+    return out
+
+
+def lift_bwd(gout, rc, bidx, shape, channels_last):
+    gout = _chk(gout, torch.float32, "gout")
+    b, c, h, w = shape
+    mf = torch.channels_last if channels_last else torch.contiguous_format
+    gmap = torch.zeros(shape, dtype=torch.float32, device=gout.device, memory_format=mf)
+    sb, sc, sh, sw = _fmap_strides(gmap)
+    lib().lift_bwd(gout.data_ptr(), sb, sc, sh, sw, b, c, h, w, rc.data_ptr(), bidx.data_ptr(), rc.shape[0],
+                   gmap.data_ptr(), _stream())
+    return gmap
+
+
+# ----------------------------------------------------------------------------- sparse convolution
+def conv_gather_f32(inp, nbr, k, kflip, w, w_transposed):
+    """out[j] = sum_k inp[nbr[j,k]] @ (W[k] or W[k]^T), fp32 CUDA-core path."""
+    inp = _chk(inp, torch.float32, "inp")
+    nbr = _chk(nbr, torch.int32, "nbr")
+    w = _chk(w, torch.float32, "w")
+    n_out, kpad = nbr.shape
+    cin, cout = w.shape[-2], w.shape[-1]
+    red, ncols = (cout, cin) if w_transposed else (cin, cout)
+    if inp.shape[1] != red:
+        raise Ft3dError("conv: feature width %d != %d" % (inp.shape[1], red))
+    out = torch.empty((n_out, ncols), dtype=torch.float32, device=inp.device)
+    lib().conv_gather_f32(inp.data_ptr(), nbr.data_ptr(), n_out, k, kpad, int(kflip), red, ncols, w.data_ptr(),
+                          int(w_transposed), out.data_ptr(), _stream())
+    return out
+
+
+def conv_wgrad_f32(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
+    a = _chk(a, torch.float32, "a")
+    b = _chk(b, torch.float32, "b")
+    gw = torch.zeros((k, cin, cout), dtype=torch.float32, device=a.device)
+    lib().conv_wgrad_f32(a.data_ptr(), b.data_ptr(), pairs.data_ptr(), pair_offsets.data_ptr(), k, int(ca), cin,
+                         cout, int(max_pairs), gw.data_ptr(), _stream())
+    return gw
+
+
+_PACK_CACHE = {}
+
+
+def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Tensor:
+    """bf16 swizzled weight image for the tcgen05 kernels, cached per parameter version (repacked only after
+    an optimizer step changed the weights)."""
+    w = _chk(w, torch.float32, "w")
+    key = (w.data_ptr(), bool(w_transposed), tuple(w.shape))
+    ver = (owner if owner is not None else w)._version
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    k, cin, cout = w.shape
+    red, ncols = (cout, cin) if w_transposed else (cin, cout)
+    nbytes = lib().conv_packed_bytes(k, red, ncols)
+    img = hit[1] if hit is not None else torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    lib().conv_pack_weights(w.data_ptr(), k, cin, cout, int(w_transposed), img.data_ptr(), _stream())
+    _PACK_CACHE[key] = (ver, img)
+    return img
+
+
+def conv_gather_tc(inp, nbr, k, kflip, w, w_transposed, owner=None):
+    """Same contract as conv_gather_f32 on the tcgen05 tensor cores (bf16 operands, fp32 accumulate)."""
+    inp = _chk(inp, torch.float32, "inp")
+    nbr = _chk(nbr, torch.int32, "nbr")
+    n_out, kpad = nbr.shape
+    cin, cout = w.shape[-2], w.shape[-1]
+    red, ncols = (cout, cin) if w_transposed else (cin, cout)
+    if inp.shape[1] != red:
+        raise Ft3dError("conv: feature width %d != %d" % (inp.shape[1], red))
+    img = packed_weights(w, w_transposed, owner)
+    out = torch.empty((n_out, ncols), dtype=torch.float32, device=inp.device)
+    lib().conv_gather_tc(inp.data_ptr(), nbr.data_ptr(), n_out, k, kpad, int(kflip), red, ncols, img.data_ptr(),
+                         out.data_ptr(), _stream())
+    return out
+
+
+def conv_wgrad_tc(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
+    a = _chk(a, torch.float32, "a")
+    b = _chk(b, torch.float32, "b")
+    gw = torch.zeros((k, cin, cout), dtype=torch.float32, device=a.device)
+    lib().conv_wgrad_tc(a.data_ptr(), b.data_ptr(), pairs.data_ptr(), pair_offsets.data_ptr(), k, int(ca), cin,
+                        cout, int(max_pairs), gw.data_ptr(), _stream())
+    return gw

@@ -144,7 +144,9 @@ int ft3d_conv_gather_f32(const float* in, const int32_t* nbr, int64_t n_out, int
                          int32_t kpad, int32_t kflip, int32_t red, int32_t ncols, const float* w,
                          int32_t w_transposed, float* out, ft3d_stream_t stream);
 /* bf16 tcgen05 variant: operands rounded to bf16, fp32 accumulation in TMEM.  `wpacked` is the
- * image written by ft3d_conv_pack_weights for the same (K, red, ncols, w_transposed). */
+ * image written by ft3d_conv_pack_weights for the same (K, cin, cout, w_transposed): per offset and
+ * 64-wide reduction block one [ncols x 128 B] swizzled bf16 tile, streamed with cp.async.bulk.
+ * Supported: red % 16 == 0 (16..512), ncols % 32 == 0 (32..256, or 384). */
 size_t ft3d_conv_packed_bytes(int32_t K, int32_t red, int32_t ncols);
 int ft3d_conv_pack_weights(const float* w, int32_t K, int32_t cin, int32_t cout,
                            int32_t w_transposed, void* wpacked, ft3d_stream_t stream);
@@ -162,11 +164,6 @@ int ft3d_conv_wgrad_f32(const float* a, const float* b, const int32_t* pairs,
 int ft3d_conv_wgrad_tc(const float* a, const float* b, const int32_t* pairs,
                        const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
                        int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
-
-/* ---- self-test of the tcgen05 building block (tests only): D[128,n] = A[128,kdim] B[n,kdim]^T
- * with bf16 operands in the layouts the conv kernels use.  mode 0 = K-major, 1 = MN-major. */
-int ft3d_umma_selftest(const float* a, const float* b, int32_t n, int32_t kdim, int32_t mode,
-                       float* d, ft3d_stream_t stream);
 
 #ifdef __cplusplus
 }

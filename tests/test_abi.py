@@ -1,0 +1,58 @@
+"""The C-ABI boundary: libft3d.so loads on a CPU-only box and exports every symbol include/ft3d.h declares."""
+import ctypes
+import os
+
+import pytest
+
+from fusiontransformer_b200 import _lib
+
+
+def test_header_parses():
+    protos = _lib.parse_header()
+    assert len(protos) >= 30
+    for must in ("ft3d_hash", "ft3d_quantize", "ft3d_kmap_build", "ft3d_kmap_pairs", "ft3d_conv_gather_tc",
+                 "ft3d_conv_wgrad_tc", "ft3d_conv_gather_f32", "ft3d_devoxelize_fwd", "ft3d_lift_fwd",
+                 "ft3d_last_error", "ft3d_version"):
+        assert must in protos, must
+    res, args = protos["ft3d_hash"]
+    assert res is ctypes.c_int and args == [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+
+
+def test_library_exports_every_declared_symbol():
+    if not _lib.LIB_PATH.exists():
+        from fusiontransformer_b200.build import build_library
+        build_library()
+    cdll = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in _lib.parse_header():
+        assert hasattr(cdll, name), "libft3d.so does not export %s" % name
+    cdll.ft3d_version.restype = ctypes.c_int
+    assert cdll.ft3d_version() == 100
+
+
+def test_host_only_entry_points():
+    L = _lib.lib()
+    assert L.table_capacity(1000) == 2048 and L.table_capacity(0) == 1024
+    assert L.conv_packed_bytes(27, 96, 128) == 27 * 2 * 128 * 128
+    assert L.unique_workspace(1000) > 1000 * 8
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    with pytest.raises(_lib.Ft3dError, match="bad K"):
+        L.conv_gather_tc(16, 16, 10, 40, 32, 0, 64, 64, 16, 16, None)
+    with pytest.raises(_lib.Ft3dError, match="unsupported shape"):
+        L.conv_gather_tc(16, 16, 10, 27, 32, 0, 20, 64, 16, 16, None)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from fusiontransformer_b200 import ops
+    with pytest.raises(_lib.Ft3dError, match="CUDA tensor"):
+        ops.hash_coords(torch.zeros(4, 4, dtype=torch.int32))
+
+
+def test_product_does_not_import_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "fusiontransformer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

@@ -1,0 +1,65 @@
+"""Host-side logic that needs no GPU: containers, alias installation, KernelRegion, model key parity."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_alias_exposes_reference_import_surface():
+    import fusiontransformer_b200 as ft
+    ft.install_as_torchsparse()
+    import torchsparse
+    import torchsparse.nn as spnn
+    import torchsparse.nn.functional as spf
+    from torchsparse.point_tensor import PointTensor
+    from torchsparse.sparse_tensor import SparseTensor
+    from torchsparse.utils import sparse_quantize
+    ns = {}
+    exec("from torchsparse.utils.kernel_region import *\nfrom torchsparse.utils.helpers import *", ns)
+    assert "torch" in ns and "KernelRegion" in ns       # FusionTransformer/models/utils.py relies on the leaked torch
+    for name in ("sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights", "conv3d"):
+        assert hasattr(spf, name)
+    for name in ("Conv3d", "BatchNorm", "ReLU"):
+        assert hasattr(spnn, name)
+    assert callable(torchsparse.cat) and callable(sparse_quantize)
+    st = SparseTensor(coords=torch.zeros(3, 4, dtype=torch.int32), feats=torch.zeros(3, 4))
+    st.check()
+    assert st.s == 1 and 1 in st.coord_maps
+    pt = PointTensor(st.F, st.C.float())
+    assert pt.additional_features == {"idx_query": {}, "counts": {}}
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/FusionTransformer/models/spvcnn.py"), reason="reference tree absent")
+def test_reference_spvcnn_builds_on_alias_with_same_state_dict():
+    import fusiontransformer_b200 as ft
+    ft.install_as_torchsparse()
+    sys.path.insert(0, "/root/reference")
+    try:
+        from FusionTransformer.models.spvcnn import SPVCNN as Ref
+    finally:
+        sys.path.pop(0)
+    from fusiontransformer_b200.spvcnn import SPVCNN
+    ref, ours = Ref(), SPVCNN()
+    sr, so = ref.state_dict(), ours.state_dict()
+    assert list(sr.keys()) == list(so.keys())
+    assert all(sr[k].shape == so[k].shape for k in sr)
+    assert sum(p.numel() for p in ours.parameters()) == 21776160
+
+
+def test_kernel_region_matches_oracle():
+    from fusiontransformer_b200.utils import KernelRegion
+    from oracle import ts_ops as ts
+    for ks in (1, 2, 3):
+        for s in (1, 2, 8):
+            assert torch.equal(KernelRegion(ks, s).get_kernel_offset(), ts.KernelRegion(ks, s).get_kernel_offset())
+
+
+def test_conv3d_parameter_layout():
+    from fusiontransformer_b200 import nn as spnn
+    assert spnn.Conv3d(32, 64, 3).kernel.shape == (27, 32, 64)
+    assert spnn.Conv3d(32, 64, 2, stride=2, transpose=True).kernel.shape == (8, 32, 64)
+    assert spnn.Conv3d(32, 64, 1).kernel.shape == (32, 64)
+    c = spnn.Conv3d(16, 8, 3)
+    assert c.kernel.abs().max() <= 1.0 / (16 * 27) ** 0.5 + 1e-7
