@@ -60,6 +60,8 @@ class _Lib:
                 "(there is no CPU or PyTorch fallback)" % LIB_PATH)
         self.cdll = ctypes.CDLL(str(LIB_PATH))
         self.protos = parse_header()
+        self.calls = {}          # entry point -> number of calls (bench.py turns this into a launch count)
+        self.profile = None      # when a list: (entry point, start event, end event) appended per call
         for name, (res, args) in self.protos.items():
             try:
                 fn = getattr(self.cdll, name)
@@ -73,9 +75,19 @@ class _Lib:
 
     def _checked(self, fn, name):
         last_error = self.cdll.ft3d_last_error
+        short = name[len("ft3d_"):]
 
         def call(*a):
+            self.calls[short] = self.calls.get(short, 0) + 1
+            prof = self.profile
+            if prof is not None:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = fn(*a)
+            if prof is not None:
+                e1.record()
+                prof.append((short, e0, e1))
             if rc != 0:
                 last_error.restype = ctypes.c_char_p
                 raise Ft3dError("%s failed (%d): %s" % (name, rc, (last_error() or b"").decode()))
@@ -91,3 +103,18 @@ def lib() -> _Lib:
     if _lib is None:
         _lib = _Lib()
     return _lib
+
+
+# CUDA kernels launched by one call of each entry point (fixed by csrc/*.cu; cub passes counted from its
+# onesweep/scan implementations).  Used only to report `gpu_launches`.
+LAUNCHES = {
+    "hash": 1, "kernel_hash": 1, "scale_coords": 3, "quantize": 14, "unique": 9, "coarsen_hash": 1,
+    "gather_rows_i32": 1, "table_build": 2, "table_query": 1, "kmap_build": 1, "kmap_pairs": 3, "kmap_transpose": 2,
+    "count": 2, "voxelize_fwd": 2, "voxelize_bwd": 1, "devoxelize_fwd": 1, "devoxelize_bwd": 2, "ti_weights": 1,
+    "v2p_build": 1, "p2v_build": 2, "lift_fwd": 1, "lift_bwd": 1, "conv_gather_f32": 1, "conv_wgrad_f32": 1,
+    "conv_pack_weights": 1, "conv_gather_tc": 1, "conv_wgrad_tc": 1,
+}
+
+
+def launch_count(calls: dict) -> int:
+    return sum(LAUNCHES.get(k, 1) * v for k, v in calls.items())

@@ -27,10 +27,19 @@ def _tc_ok(red: int, ncols: int) -> bool:
             and (32 <= ncols <= 256 or ncols == 384))
 
 
+WORK_LOG = None   # when a list: one dict per conv launch (kind, pairs, red, ncols, rows) for bench.py's roofline
+
+
+def _log(kind, kmap, red, ncols, rows):
+    if WORK_LOG is not None:
+        WORK_LOG.append(dict(kind=kind, pairs=kmap.num_pairs(), red=red, ncols=ncols, rows=rows, K=kmap.K))
+
+
 def gather_conv(inp, table, kmap, kernel, kflip: bool, w_transposed: bool):
     """out[j] = sum_k inp[table[j,k]] @ (W[k] | W[k]^T); forward, dgrad and transposed conv share it."""
     cin, cout = kernel.shape[-2], kernel.shape[-1]
     red, ncols = (cout, cin) if w_transposed else (cin, cout)
+    _log("conv_gather_tc" if _tc_ok(red, ncols) else "conv_gather_f32", kmap, red, ncols, table.shape[0])
     w = kernel.detach()
     if w.dim() == 2:
         w = w.unsqueeze(0)
@@ -43,6 +52,8 @@ def wgrad(feats, gout, kmap, cin: int, cout: int, transpose: bool):
     pairs, offsets = kmap.pairs_padded, kmap.pair_offsets
     max_pairs = kmap.num_pairs()
     ca = 1 if transpose else 0
-    if mode() == "tc" and cin % 16 == 0 and 16 <= cin <= 512 and cout % 32 == 0 and 32 <= cout <= 256:
+    tc = mode() == "tc" and cin % 16 == 0 and 16 <= cin <= 512 and cout % 32 == 0 and 32 <= cout <= 256
+    _log("conv_wgrad_tc" if tc else "conv_wgrad_f32", kmap, cin, cout, max_pairs)
+    if tc:
         return ops.conv_wgrad_tc(feats, gout, pairs, offsets, kmap.K, ca, cin, cout, max_pairs)
     return ops.conv_wgrad_f32(feats, gout, pairs, offsets, kmap.K, ca, cin, cout, max_pairs)

@@ -1,0 +1,107 @@
+"""Data-parallel gradient exchange for the 3D branch (the reference's only parallelism).
+
+Reference: DistributedDataParallel(model, find_unused_parameters=True) at
+FusionTransformer/modules/TorchpackInterface.py:78-81 -- shard by scan, per-rank BatchNorm statistics, one
+gradient allreduce(sum)/world per step.  Here: one process per GPU (torchrun), all gradients live in ONE flat fp32
+arena laid out in reverse registration order (the order backward produces them), parameters' ``.grad`` are views
+into it, and each bucket's NCCL all-reduce is launched on a side stream the moment its last gradient has been
+accumulated, overlapping the remaining dgrad/wgrad kernels.  Parameters that received no gradient (unused heads)
+contribute zeros, which is what ``find_unused_parameters=True`` amounts to.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20, process_group=None, overlap: bool = True):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        order = list(reversed(self.params))
+        total = sum(p.numel() for p in order)
+        dev = order[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.buckets = []            # (start, end) element ranges of the arena
+        self._bucket_of = {}
+        self._pending = []
+        off, bstart, bidx = 0, 0, 0
+        for p in order:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[p] = bidx
+            off += n
+            if (off - bstart) * 4 >= bucket_bytes:
+                self.buckets.append((bstart, off))
+                bstart, bidx = off, bidx + 1
+        if off > bstart:
+            self.buckets.append((bstart, off))
+        self._need = [0] * len(self.buckets)
+        for p in order:
+            self._need[self._bucket_of[p]] += 1
+        self._seen = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self.overlap = overlap and self.world > 1 and dev.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
+        self._works = []
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    # -- broadcast initial parameters/buffers from rank 0 (what DDP's constructor does)
+    def broadcast_parameters(self, module: torch.nn.Module):
+        if self.world == 1:
+            return
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, 0, group=self.group)
+
+    def zero_grad(self):
+        self.flat.zero_()
+        self._seen = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+
+    def _launch(self, b: int):
+        if self._launched[b]:
+            return
+        self._launched[b] = True
+        s, e = self.buckets[b]
+        view = self.flat[s:e]
+        if self.overlap:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _hook(self, p):
+        b = self._bucket_of[p]
+        self._seen[b] += 1
+        if self._seen[b] == self._need[b]:
+            self._launch(b)
+
+    def finish(self):
+        """Call after backward: launches buckets with unused parameters, waits, and averages over ranks."""
+        if self.world == 1:
+            return
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        self.flat.mul_(1.0 / self.world)
+
+
+def shard_indices(num_items: int, rank: int, world: int, epoch: int = 0, shuffle: bool = False, seed: int = 0):
+    """DistributedSampler semantics of FusionTransformer/data/build.py:62-67: pad to a multiple of world by
+    wrapping, then take every world-th index starting at rank."""
+    if shuffle:
+        g = torch.Generator().manual_seed(seed + epoch)
+        idx = torch.randperm(num_items, generator=g).tolist()
+    else:
+        idx = list(range(num_items))
+    total = (num_items + world - 1) // world * world
+    idx += idx[: total - len(idx)]
+    return idx[rank:total:world]

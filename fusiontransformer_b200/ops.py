@@ -279,7 +279,7 @@ def lift_bwd(gout, rc, bidx, shape, channels_last):
     gout = _chk(gout, torch.float32, "gout")
     b, c, h, w = shape
     mf = torch.channels_last if channels_last else torch.contiguous_format
-    gmap = torch.zeros(shape, dtype=torch.float32, device=gout.device, memory_format=mf)
+    gmap = torch.empty(shape, dtype=torch.float32, device=gout.device, memory_format=mf).zero_()
     sb, sc, sh, sw = _fmap_strides(gmap)
     lib().lift_bwd(gout.data_ptr(), sb, sc, sh, sw, b, c, h, w, rc.data_ptr(), bidx.data_ptr(), rc.shape[0],
                    gmap.data_ptr(), _stream())
@@ -316,20 +316,26 @@ _PACK_CACHE = {}
 
 
 def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Tensor:
-    """bf16 swizzled weight image for the tcgen05 kernels, cached per parameter version (repacked only after
-    an optimizer step changed the weights)."""
+    """bf16 swizzled weight image for the tcgen05 kernels.  Cached per owning tensor object and version counter:
+    repacked only after an in-place update (optimizer step) or when a different tensor is passed; entries die
+    with their owner (weak reference), so a recycled device address can never alias a stale image."""
+    import weakref
     w = _chk(w, torch.float32, "w")
-    key = (w.data_ptr(), bool(w_transposed), tuple(w.shape))
-    ver = (owner if owner is not None else w)._version
+    owner = w if owner is None else owner
+    key = (id(owner), bool(w_transposed))
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    if hit is not None and hit[0]() is owner and hit[1] == owner._version and hit[2] == w.data_ptr():
+        return hit[3]
     k, cin, cout = w.shape
     red, ncols = (cout, cin) if w_transposed else (cin, cout)
     nbytes = lib().conv_packed_bytes(k, red, ncols)
-    img = hit[1] if hit is not None else torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    reuse = hit is not None and hit[0]() is owner and hit[3].numel() == nbytes
+    img = hit[3] if reuse else torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     lib().conv_pack_weights(w.data_ptr(), k, cin, cout, int(w_transposed), img.data_ptr(), _stream())
-    _PACK_CACHE[key] = (ver, img)
+    if len(_PACK_CACHE) > 512:
+        for kk in [kk for kk, v in _PACK_CACHE.items() if v[0]() is None]:
+            del _PACK_CACHE[kk]
+    _PACK_CACHE[key] = (weakref.ref(owner), owner._version, w.data_ptr(), img)
     return img
 
 

@@ -68,14 +68,20 @@ def test_train_step_gradients(monkeypatch, small_batch, fusion, mode, tol):
     assert rel_l2(og_["lidar_seg_logit"], oo["lidar_seg_logit"]) < tol
     assert abs(lg.item() - lo.item()) < tol * max(1.0, abs(lo.item()))
     po = dict(o.named_parameters())
-    worst = 0.0
+    # A Linear bias that feeds a BatchNorm has an exactly-zero true gradient (numerical noise on both sides), so
+    # each tensor's error is measured against max(its own norm, 1e-4 x the largest gradient norm in the net).
+    gmax = max(p.grad.norm().item() for p in o.parameters() if p.grad is not None)
+    worst, worst_name = 0.0, None
     for name, p in m.named_parameters():
         if po[name].grad is None:
             assert p.grad is None or p.grad.abs().max() == 0, name
             continue
-        worst = max(worst, rel_l2(p.grad, po[name].grad))
+        go = po[name].grad.double()
+        err = ((p.grad.double().cpu() - go).norm() / max(go.norm().item(), 1e-4 * gmax)).item()
+        if err > worst:
+            worst, worst_name = err, name
     # gradients pass through ~50 batch-norms; the bound is on the worst single tensor
-    assert worst < 20 * tol, worst
+    assert worst < 20 * tol, (worst_name, worst)
 
 
 def test_reference_model_files_run_unmodified():
