@@ -57,3 +57,59 @@ def wgrad(feats, gout, kmap, cin: int, cout: int, transpose: bool):
     if tc:
         return ops.conv_wgrad_tc(feats, gout, pairs, offsets, kmap.K, ca, cin, cout, max_pairs)
     return ops.conv_wgrad_f32(feats, gout, pairs, offsets, kmap.K, ca, cin, cout, max_pairs)
+
+
+# ------------------------------------------------------------------------------------------ pair-major tcgen05 path
+def pairs_ok(cin: int, cout: int) -> bool:
+    """Both the forward (red=cin, ncols=cout), the dgrad (red=cout, ncols=cin) and the wgrad shape must be covered."""
+    def gemm_ok(red, ncols):
+        return red % 16 == 0 and 16 <= red <= 512 and ncols % 32 == 0 and (32 <= ncols <= 256 or ncols == 384)
+    return (mode() == "tc" and os.environ.get("FT3D_CONV_ALGO", "pairs") == "pairs" and gemm_ok(cin, cout)
+            and gemm_ok(cout, cin) and cout <= 256)
+
+
+def pairs_conv(x16, kmap, kernel, role: str):
+    """role: forward | dgrad | transposed | dgrad_transposed (which side of the map is gathered / scattered)."""
+    w = kernel.detach()
+    K, L = kmap.K, kmap.num_pairs()
+    pairs, offsets = kmap.pairs_padded, kmap.pair_offsets
+    cin, cout = w.shape[-2], w.shape[-1]
+    if role == "forward":
+        gcol, ppos, wt, ncols = 0, kmap.ppos, False, cout
+    elif role == "dgrad":
+        gcol, ppos, wt, ncols = 1, kmap.pposT, True, cin
+    elif role == "transposed":       # out = fine rows (pair column 0), gather coarse rows (column 1)
+        gcol, ppos, wt, ncols = 1, kmap.pposT, False, cout
+    elif role == "dgrad_transposed":
+        gcol, ppos, wt, ncols = 0, kmap.ppos, True, cin
+    else:
+        raise ValueError(role)
+    red = cout if wt else cin
+    if WORK_LOG is not None:
+        WORK_LOG.append(dict(kind="conv_pairs_tc", pairs=L, red=red, ncols=ncols, rows=ppos.shape[0], K=K))
+    partial = ops.conv_pairs_tc(x16, pairs, offsets, K, gcol, L, w, wt, owner=kernel)
+    return ops.conv_reduce(partial, ppos, K, ncols)
+
+
+def pairs_wgrad(x16, g16, kmap, cin: int, cout: int, transpose: bool):
+    L = kmap.num_pairs()
+    if WORK_LOG is not None:
+        WORK_LOG.append(dict(kind="conv_wgrad_pairs_tc", pairs=L, red=cin, ncols=cout, rows=L, K=kmap.K))
+    return ops.conv_wgrad_pairs_tc(x16, g16, kmap.pairs_padded, kmap.pair_offsets, kmap.K, 1 if transpose else 0,
+                                   cin, cout, L)
+
+
+def dense_conv(x16, kernel, w_transposed: bool):
+    w = kernel.detach().unsqueeze(0)
+    n = x16.shape[0]
+    if WORK_LOG is not None:
+        WORK_LOG.append(dict(kind="conv_pairs_tc", pairs=n, red=x16.shape[1],
+                             ncols=w.shape[1] if w_transposed else w.shape[2], rows=n, K=1))
+    return ops.conv_pairs_tc(x16, None, None, 1, 0, n, w, w_transposed, owner=kernel)[:n]
+
+
+def dense_wgrad(x16, g16, cin: int, cout: int):
+    n = x16.shape[0]
+    if WORK_LOG is not None:
+        WORK_LOG.append(dict(kind="conv_wgrad_pairs_tc", pairs=n, red=cin, ncols=cout, rows=n, K=1))
+    return ops.conv_wgrad_pairs_tc(x16, g16, None, None, 1, 0, cin, cout, n).view(cin, cout)

@@ -1,0 +1,466 @@
+// Pair-major sparse convolution on tcgen05 tensor cores: gather -> GEMM -> sorted, atomic-free scatter.
+//
+// LiDAR kernel maps are sparse (2-8 of the 27 offsets occupied per voxel), so the work is organised by the
+// reference's own pair lists: for offset k the L_k (in,out) pairs form dense 128-row GEMM tiles
+//     P[p, :] = in[pairs[p].gather, :] @ B_k          (bf16 operands, fp32 accumulation in TMEM)
+// and every pair's partial row lands at its position p in the offset-major pair order.  A second, purely
+// HBM-bound pass sums the (at most K) partial rows of each output voxel in fixed offset order through the
+// pair-position table ppos[row][k] -- a sorted segmented reduction: deterministic, no atomics, each output row
+// written once.  MMA work and operand traffic scale with the number of pairs, not with 27 x voxels.
+//
+// Stage pipeline of one CTA (= one tile of 128 pairs of one offset; red/64 stages):
+//   warps 0-3  issue cp.async 16-byte gathers of bf16 feature rows straight into the 128B-swizzled A block and
+//              arm the stage's mbarrier with cp.async.mbarrier.arrive.noinc (no register staging, every stage of
+//              the tile in flight at once); afterwards they are the epilogue (tcgen05.ld -> P rows);
+//   warp 4     streams the pre-packed weight block with cp.async.bulk (TMA unit) onto the same mbarrier;
+//   warp 5     one lane issues tcgen05.mma 128 x ncols x 16 and commits.
+// The same kernel runs dense GEMMs (k = 1 convolutions) with an identity gather (pairs == nullptr).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ft3d {
+using namespace tc;
+
+constexpr int kPThreads = 192;
+constexpr int kPProducers = 128;
+constexpr int kPMaxStages = 8;
+
+struct PairsSmemHeader {
+  uint64_t full[kPMaxStages];
+  uint64_t empty[kPMaxStages];
+  uint64_t accum_full;
+  uint32_t tmem_base;
+  int32_t idx[kTileRows];
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// tile -> (offset k, [begin,end) in the pair list); tiles never straddle offsets
+__device__ __forceinline__ bool pair_tile(const int32_t* __restrict__ off, int K, int item, int rows, int* k_out,
+                                          int* begin, int* end) {
+  int acc = 0;
+  for (int k = 0; k < K; ++k) {
+    int b = __ldg(off + k), e = __ldg(off + k + 1);
+    int nt = (e - b + rows - 1) / rows;
+    if (item < acc + nt) {
+      *k_out = k;
+      *begin = b + (item - acc) * rows;
+      *end = min(*begin + rows, e);
+      return true;
+    }
+    acc += nt;
+  }
+  return false;
+}
+
+// gather one [128 x nchunk*16B] swizzled block of bf16 rows with cp.async (zero-fill for idx < 0)
+__device__ __forceinline__ void gather_block_bf16(uint8_t* block, const __nv_bfloat16* __restrict__ src, int row_width,
+                                                  int col0, int nchunk, int tid, const int32_t* __restrict__ s_idx) {
+  const uint32_t base = smem_u32(block);
+  const int total = kTileRows * nchunk;
+  for (int q = tid; q < total; q += kPProducers) {
+    const int r = q / nchunk;
+    const int c = q - r * nchunk;
+    const int g = s_idx[r];
+    const __nv_bfloat16* p = src + (g >= 0 ? (int64_t)g * row_width + col0 + c * 8 : 0);
+    cp_async_16(base + r * kBlockRowBytes + ((c ^ (r & 7)) << 4), p, g >= 0 ? 16u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(kPThreads)
+conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restrict__ pairs,
+                     const int32_t* __restrict__ off, int K, int gather_col, int64_t n_identity, int red, int ncols,
+                     const uint8_t* __restrict__ wpacked, float* __restrict__ P, int nstages, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nkb = (red + 63) / 64;
+  const int b_bytes = ncols * kBlockRowBytes;
+  const int stage_bytes = kBlockBytes + b_bytes;
+  PairsSmemHeader* hdr = (PairsSmemHeader*)(smem + (size_t)nstages * stage_bytes);   // ring: nstages <= nkb
+
+  int k = 0, begin, end;
+  if (pairs != nullptr) {
+    if (!pair_tile(off, K, blockIdx.x, kTileRows, &k, &begin, &end)) return;   // uniform per CTA
+  } else {
+    begin = blockIdx.x * kTileRows;
+    end = (int)min((int64_t)begin + kTileRows, n_identity);
+    if (begin >= end) return;
+  }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&hdr->full[s], kPProducers + 1);
+      mbar_init(&hdr->empty[s], 1);
+    }
+    mbar_init(&hdr->accum_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)tmem_cols);
+  if (tid < kPProducers) {
+    const int p = begin + tid;
+    int g = -1;
+    if (p < end) {
+      if (pairs != nullptr) {
+        int2 pr = __ldg(pairs + p);
+        g = gather_col ? pr.y : pr.x;
+      } else {
+        g = p;
+      }
+    }
+    hdr->idx[tid] = g;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  if (warp < 4) {
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % nstages;
+      if (kb >= nstages) mbar_wait(&hdr->empty[s], ((uint32_t)(kb / nstages) & 1) ^ 1);
+      const int width = red - kb * 64 < 64 ? red - kb * 64 : 64;
+      gather_block_bf16(smem + (size_t)s * stage_bytes, in, red, kb * 64, width >> 3, tid, hdr->idx);
+      cp_async_arrive_noinc(&hdr->full[s]);
+    }
+    // epilogue: TMEM lane = pair row of the tile
+    mbar_wait(&hdr->accum_full, 0);
+    tc_fence_after();
+    const int p = begin + tid;
+    float* prow = P + (int64_t)p * ncols;
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (p < end) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % nstages;
+        if (kb >= nstages) mbar_wait(&hdr->empty[s], ((uint32_t)(kb / nstages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&hdr->full[s], (uint32_t)b_bytes);
+        bulk_g2s(smem + (size_t)s * stage_bytes + kBlockBytes, wpacked + ((size_t)k * nkb + kb) * b_bytes,
+                 (uint32_t)b_bytes, &hdr->full[s]);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const int nchunks = ncols > 256 ? 2 : 1;
+      const int ncw = ncols / nchunks;
+      const uint32_t idesc = umma_idesc_bf16(128, ncw, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % nstages;
+        mbar_wait(&hdr->full[s], (uint32_t)(kb / nstages) & 1);
+        fence_proxy_async_smem();          // cp.async (generic proxy) data -> tensor-core (async proxy) reads
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + kBlockBytes;
+        const int ksteps = (red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t da = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+          for (int c = 0; c < nchunks; ++c) {
+            const uint64_t db = smem_desc_sw128(b_addr + c * ncw * kBlockRowBytes + kk * 32, 16, 1024);
+            umma_bf16(tmem_base + (uint32_t)(c * ncw), da, db, idesc, (kb | kk) != 0);
+          }
+        }
+        if (kb + nstages < nkb) umma_commit(&hdr->empty[s]);
+      }
+      umma_commit(&hdr->accum_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ sorted scatter
+// out[row,:] = sum over k (ascending) of P[ppos[row,k],:]  -- one thread per (row, 4 channels)
+__global__ void conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos, int64_t n_rows, int K,
+                                   int kpad, int ncols, float* __restrict__ out) {
+  const int cv = ncols >> 2;
+  const int64_t total = n_rows * cv;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / cv;
+    const int ch = (int)(t - row * cv) << 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int32_t* pr = ppos + row * kpad;
+    for (int k = 0; k < K; ++k) {
+      const int p = __ldg(pr + k);
+      if (p >= 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(P + (int64_t)p * ncols + ch));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    *reinterpret_cast<float4*>(out + row * ncols + ch) = acc;
+  }
+}
+
+// pposT[gather-side row][k] = pair position, for the role-swapped use of a map (dgrad, transposed conv)
+__global__ void pair_positions_kernel(const int2* __restrict__ pairs, const int32_t* __restrict__ off, int K, int kpad,
+                                      int col, int32_t* __restrict__ ppos) {
+  const int total = __ldg(off + K);
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < K && p >= __ldg(off + k + 1)) ++k;
+    const int2 pr = __ldg(pairs + p);
+    ppos[(int64_t)(col ? pr.y : pr.x) * kpad + k] = p;
+  }
+}
+
+__global__ void fill_i32_kernel_p(int32_t* p, int64_t n, int32_t v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// fp32 -> bf16 (round to nearest even), 8 elements per thread
+__global__ void to_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ dst) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = n8 << 3; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad (bf16 inputs)
+constexpr int kWgPairsPerCta = 512;   // pairs reduced by one CTA = 4 stages of 128, all in flight
+constexpr int kWgStages = kWgPairsPerCta / kTileRows;
+
+struct WgSmemHeader {
+  uint64_t full[kWgStages];
+  uint64_t accum_full;
+  uint32_t tmem_base;
+  int32_t pa[kWgStages][kTileRows];
+  int32_t pb[kWgStages][kTileRows];
+};
+
+__global__ void __launch_bounds__(kPThreads)
+conv_wgrad_pairs_tc_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           const int2* __restrict__ pairs, const int32_t* __restrict__ off, int K, int ca,
+                           int64_t n_identity, int cin, int cout, float* __restrict__ gw, int nstages_fit,
+                           int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nb_blocks = (cout + 63) / 64;
+  const int stage_bytes = (2 + nb_blocks) * kBlockBytes;
+  WgSmemHeader* hdr = (WgSmemHeader*)(smem + (size_t)nstages_fit * stage_bytes);
+  const int rows_per_cta = nstages_fit * kTileRows;
+
+  int k = 0, begin, end;
+  if (pairs != nullptr) {
+    if (!pair_tile(off, K, blockIdx.x, rows_per_cta, &k, &begin, &end)) return;
+  } else {
+    begin = blockIdx.x * rows_per_cta;
+    end = (int)min((int64_t)begin + rows_per_cta, n_identity);
+    if (begin >= end) return;
+  }
+  const int mb = blockIdx.y;
+  const int m_valid = cin - mb * 128 < 128 ? cin - mb * 128 : 128;
+  const int niter = (end - begin + kTileRows - 1) / kTileRows;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < niter; ++s) mbar_init(&hdr->full[s], kPProducers);
+    mbar_init(&hdr->accum_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)tmem_cols);
+  if (tid < kPProducers) {
+    for (int s = 0; s < niter; ++s) {
+      const int p = begin + s * kTileRows + tid;
+      int ia = -1, ib = -1;
+      if (p < end) {
+        if (pairs != nullptr) {
+          int2 pr = __ldg(pairs + p);
+          ia = ca ? pr.y : pr.x;
+          ib = ca ? pr.x : pr.y;
+        } else {
+          ia = ib = p;
+        }
+      }
+      hdr->pa[s][tid] = ia;
+      hdr->pb[s][tid] = ib;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  if (warp < 4) {
+    for (int s = 0; s < niter; ++s) {
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      for (int blk = 0; blk * 64 < m_valid; ++blk) {
+        const int width = m_valid - blk * 64 < 64 ? m_valid - blk * 64 : 64;
+        gather_block_bf16(st + blk * kBlockBytes, a, cin, mb * 128 + blk * 64, width >> 3, tid, hdr->pa[s]);
+      }
+      for (int blk = 0; blk < nb_blocks; ++blk) {
+        const int width = cout - blk * 64 < 64 ? cout - blk * 64 : 64;
+        gather_block_bf16(st + (2 + blk) * kBlockBytes, b, cout, blk * 64, width >> 3, tid, hdr->pb[s]);
+      }
+      cp_async_arrive_noinc(&hdr->full[s]);
+    }
+    mbar_wait(&hdr->accum_full, 0);
+    tc_fence_after();
+    float* grow = gw + ((int64_t)k * cin + mb * 128 + tid) * cout;
+    for (int c0 = 0; c0 < cout; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (tid < m_valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(grow + c0 + j),
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                __uint_as_float(v[j + 3])));
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, cout, 1, 1);
+      for (int s = 0; s < niter; ++s) {
+        mbar_wait(&hdr->full[s], 0);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + 2 * kBlockBytes;
+        for (int kk = 0; kk < kTileRows / 16; ++kk) {
+          const uint64_t da = smem_desc_sw128(a_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
+          const uint64_t db = smem_desc_sw128(b_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (s | kk) != 0);
+        }
+      }
+      umma_commit(&hdr->accum_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+static int tmem_cols_pow2(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+}  // namespace ft3d
+
+using namespace ft3d;
+
+extern "C" {
+
+int ft3d_to_bf16(const float* src, int64_t n, void* dst, ft3d_stream_t stream) {
+  if (n == 0) return FT3D_OK;
+  FT3D_REQUIRE(src && dst && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "ft3d_to_bf16: bad arguments");
+  to_bf16_kernel<<<grid_for((n >> 3) + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, n, (__nv_bfloat16*)dst);
+  return check_launch("ft3d_to_bf16");
+}
+
+int ft3d_kmap_pair_positions(const int32_t* pairs, const int32_t* pair_offsets, int32_t K, int32_t kpad, int32_t col,
+                             int64_t n_rows, int64_t max_pairs, int32_t* ppos_out, ft3d_stream_t stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FT3D_REQUIRE(K > 0 && K <= kpad && (col == 0 || col == 1), "ft3d_kmap_pair_positions: bad arguments");
+  if (n_rows > 0) {
+    FT3D_REQUIRE(ppos_out != nullptr, "ft3d_kmap_pair_positions: null output");
+    fill_i32_kernel_p<<<grid_for(n_rows * kpad, 256), 256, 0, s>>>(ppos_out, n_rows * kpad, -1);
+  }
+  if (n_rows > 0 && max_pairs > 0) {
+    FT3D_REQUIRE(pairs && pair_offsets, "ft3d_kmap_pair_positions: null input");
+    pair_positions_kernel<<<grid_for(max_pairs, 256), 256, 0, s>>>((const int2*)pairs, pair_offsets, K, kpad, col,
+                                                                   ppos_out);
+  }
+  return check_launch("ft3d_kmap_pair_positions");
+}
+
+int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t* pair_offsets, int32_t K,
+                       int32_t gather_col, int64_t max_pairs, int32_t red, int32_t ncols, const void* wpacked,
+                       float* partial_out, ft3d_stream_t stream) {
+  if (max_pairs == 0) return FT3D_OK;
+  FT3D_REQUIRE(in_bf16 && wpacked && partial_out && K > 0 && K <= 32, "ft3d_conv_pairs_tc: bad arguments");
+  FT3D_REQUIRE((pairs == nullptr) == (pair_offsets == nullptr), "ft3d_conv_pairs_tc: pairs and pair_offsets go together");
+  FT3D_REQUIRE(pairs != nullptr || K == 1, "ft3d_conv_pairs_tc: identity gather needs K == 1");
+  FT3D_REQUIRE(red >= 16 && red % 16 == 0 && red <= 512 && ncols >= 32 && ncols % 32 == 0 &&
+                   (ncols <= 256 || ncols == 384),
+               "ft3d_conv_pairs_tc: unsupported shape red=%d ncols=%d", red, ncols);
+  FT3D_REQUIRE(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)partial_out & 15) == 0 && ((uintptr_t)wpacked & 15) == 0,
+               "ft3d_conv_pairs_tc: pointers must be 16-byte aligned");
+  const int nkb = (red + 63) / 64;
+  const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes;
+  const int tail = (int)sizeof(PairsSmemHeader) + 1024;
+  int nstages = (226 * 1024 - tail) / stage_bytes;
+  if (nstages > nkb) nstages = nkb;
+  FT3D_REQUIRE(nstages >= 1, "ft3d_conv_pairs_tc: red=%d ncols=%d does not fit shared memory", red, ncols);
+  const int smem_bytes = nstages * stage_bytes + tail;
+  static int configured = 0;
+  if (!configured) {
+    FT3D_CUDA(cudaFuncSetAttribute(conv_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 1;
+  }
+  const int64_t tiles = (max_pairs + tc::kTileRows - 1) / tc::kTileRows + (pairs ? K : 0);
+  conv_pairs_tc_kernel<<<(unsigned)tiles, kPThreads, smem_bytes, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in_bf16, (const int2*)pairs, pair_offsets, K, gather_col, max_pairs, red, ncols,
+      (const uint8_t*)wpacked, partial_out, nstages, tmem_cols_pow2(ncols));
+  return check_launch("ft3d_conv_pairs_tc");
+}
+
+int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t K, int32_t kpad,
+                     int32_t ncols, float* out, ft3d_stream_t stream) {
+  if (n_rows == 0) return FT3D_OK;
+  FT3D_REQUIRE(ppos && out && K > 0 && K <= kpad && ncols > 0 && ncols % 4 == 0, "ft3d_conv_reduce: bad arguments");
+  FT3D_REQUIRE(((uintptr_t)partial & 15) == 0 && ((uintptr_t)out & 15) == 0, "ft3d_conv_reduce: alignment");
+  conv_reduce_kernel<<<grid_for(n_rows * (ncols >> 2), 256), 256, 0, (cudaStream_t)stream>>>(partial, ppos, n_rows, K,
+                                                                                            kpad, ncols, out);
+  return check_launch("ft3d_conv_reduce");
+}
+
+int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32_t* pairs,
+                             const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin, int32_t cout,
+                             int64_t max_pairs, float* gw, ft3d_stream_t stream) {
+  if (max_pairs == 0) return FT3D_OK;
+  FT3D_REQUIRE(a_bf16 && b_bf16 && gw && K > 0, "ft3d_conv_wgrad_pairs_tc: bad arguments");
+  FT3D_REQUIRE((pairs == nullptr) == (pair_offsets == nullptr) && (pairs != nullptr || K == 1),
+               "ft3d_conv_wgrad_pairs_tc: identity gather needs K == 1 and no offsets");
+  FT3D_REQUIRE(cin >= 16 && cin % 16 == 0 && cin <= 512 && cout >= 32 && cout % 32 == 0 && cout <= 256,
+               "ft3d_conv_wgrad_pairs_tc: unsupported shape cin=%d cout=%d", cin, cout);
+  FT3D_REQUIRE(((uintptr_t)a_bf16 & 15) == 0 && ((uintptr_t)b_bf16 & 15) == 0 && ((uintptr_t)gw & 15) == 0,
+               "ft3d_conv_wgrad_pairs_tc: pointers must be 16-byte aligned");
+  const int nb_blocks = (cout + 63) / 64;
+  const int stage_bytes = (2 + nb_blocks) * tc::kBlockBytes;
+  const int tail = (int)sizeof(WgSmemHeader) + 1024;
+  // two resident CTAs when two stages of each fit in half the shared memory, else one CTA with up to 4 stages
+  int nst = (112 * 1024 - tail) / stage_bytes;
+  if (nst < 2) nst = (226 * 1024 - tail) / stage_bytes;
+  if (nst > kWgStages) nst = kWgStages;
+  FT3D_REQUIRE(nst >= 1, "ft3d_conv_wgrad_pairs_tc: tile does not fit shared memory");
+  const int smem_bytes = nst * stage_bytes + tail;
+  static int configured = 0;
+  if (!configured) {
+    FT3D_CUDA(cudaFuncSetAttribute(conv_wgrad_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 1;
+  }
+  const int rows = nst * tc::kTileRows;
+  const int64_t items = (max_pairs + rows - 1) / rows + (pairs ? K : 0);
+  dim3 grid((unsigned)items, (unsigned)((cin + 127) / 128));
+  conv_wgrad_pairs_tc_kernel<<<grid, kPThreads, smem_bytes, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs, cin,
+      cout, gw, nst, tmem_cols_pow2(cout));
+  return check_launch("ft3d_conv_wgrad_pairs_tc");
+}
+
+}  // extern "C"

@@ -90,7 +90,7 @@ kmap_scan_kernel(int32_t* __restrict__ chunk_counts, int64_t nchunks, int K, int
 __global__ void __launch_bounds__(kChunkRows)
 kmap_emit_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int K, int kpad,
                  const int32_t* __restrict__ chunk_offsets, const int32_t* __restrict__ offsets,
-                 int2* __restrict__ pairs) {
+                 int2* __restrict__ pairs, int32_t* __restrict__ ppos) {
   __shared__ int s_cnt[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * kChunkRows + threadIdx.x;
@@ -113,6 +113,9 @@ kmap_emit_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int K, int kpad
       for (int w = 0; w < warp; ++w) pos += s_cnt[w][k];
       pos += __popc(ballots[k] & ((1u << lane) - 1u));
       pairs[pos] = make_int2(vals[k], (int)row);
+      if (ppos) ppos[row * kpad + k] = pos;
+    } else if (ppos && row < n_out && k < kpad) {
+      ppos[row * kpad + k] = -1;
     }
   }
 }
@@ -161,7 +164,8 @@ size_t ft3d_kmap_pairs_workspace(int64_t n_out, int32_t kpad) {
 }
 
 int ft3d_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad, int32_t* pairs_out,
-                    int32_t* offsets_out, void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
+                    int32_t* offsets_out, int32_t* ppos_out, void* workspace, size_t workspace_bytes,
+                    ft3d_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
   FT3D_REQUIRE(offsets_out && K > 0 && K <= 32 && K <= kpad, "ft3d_kmap_pairs: bad arguments");
   if (n_out == 0) {
@@ -178,7 +182,7 @@ int ft3d_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad, 
   kmap_count_kernel<<<(unsigned)nchunks, kChunkRows, 0, s>>>(nbr, n_out, K, kpad, chunk_counts);
   kmap_scan_kernel<<<1, 1024, 0, s>>>(chunk_counts, nchunks, K, offsets_out);
   kmap_emit_kernel<<<(unsigned)nchunks, kChunkRows, 0, s>>>(nbr, n_out, K, kpad, chunk_counts, offsets_out,
-                                                            (int2*)pairs_out);
+                                                            (int2*)pairs_out, ppos_out);
   return check_launch("ft3d_kmap_pairs");
 }
 

@@ -95,6 +95,8 @@ class KernelMap:
         self._nbrT = None
         self._pairs = None
         self._offsets = None
+        self._ppos = None
+        self._pposT = None
         self._host_offsets = None
         self._event = None
         self.aux = {}               # per-map caches owned by the conv kernels (tile schedules, ...)
@@ -107,7 +109,7 @@ class KernelMap:
 
     def _build_pairs(self):
         if self._pairs is None:
-            self._pairs, self._offsets = ops.kmap_pairs(self.nbr, self.K)
+            self._pairs, self._offsets, self._ppos = ops.kmap_pairs(self.nbr, self.K)
             self._host_offsets = torch.empty(self.K + 1, dtype=torch.int32, pin_memory=True)
             self._host_offsets.copy_(self._offsets, non_blocking=True)
             self._event = torch.cuda.Event()
@@ -122,6 +124,21 @@ class KernelMap:
     def pair_offsets(self):
         self._build_pairs()
         return self._offsets
+
+    @property
+    def ppos(self):
+        """pair position of (output row, offset) -- drives the sorted scatter of the forward conv"""
+        self._build_pairs()
+        return self._ppos
+
+    @property
+    def pposT(self):
+        """pair position of (input row, offset) -- sorted scatter of dgrad / transposed conv"""
+        if self._pposT is None:
+            self._build_pairs()
+            self._pposT = ops.kmap_pair_positions(self._pairs, self._offsets, self.K, self.nbr.shape[1], 0,
+                                                  self.n_in, self.num_pairs())
+        return self._pposT
 
     def host_offsets(self):
         self._build_pairs()
@@ -175,10 +192,21 @@ def conv_mode() -> str:
 
 
 class _SparseConv(torch.autograd.Function):
+    """conv3d arithmetic.  Default (`FT3D_CONV=tc`): pair-major tcgen05 path of csrc/conv_pairs_tc.cu -- the input
+    is rounded to bf16 once (and that copy is what is saved for wgrad), partial rows are produced per pair and
+    summed per output row by the sorted scatter.  Shapes the tensor-core kernels do not cover (the 4-channel stem
+    conv) and `FT3D_CONV=f32` use the fp32 CUDA-core kernels on the same maps."""
+
     @staticmethod
     def forward(ctx, feats, kernel, kmap: KernelMap, transpose: bool):
         from . import conv_engine
         ctx.kmap, ctx.transpose = kmap, transpose
+        cin, cout = kernel.shape[-2], kernel.shape[-1]
+        ctx.pairs_path = conv_engine.pairs_ok(cin, cout)
+        if ctx.pairs_path:
+            x16 = ops.to_bf16(feats)
+            ctx.save_for_backward(x16, kernel)
+            return conv_engine.pairs_conv(x16, kmap, kernel, role="transposed" if transpose else "forward")
         ctx.save_for_backward(feats, kernel)
         table = kmap.nbrT if transpose else kmap.nbr
         return conv_engine.gather_conv(feats, table, kmap, kernel, kflip=False, w_transposed=False)
@@ -190,6 +218,13 @@ class _SparseConv(torch.autograd.Function):
         kmap, transpose = ctx.kmap, ctx.transpose
         gout = gout.contiguous()
         gin = gw = None
+        if ctx.pairs_path:
+            g16 = ops.to_bf16(gout)
+            if ctx.needs_input_grad[0]:
+                gin = conv_engine.pairs_conv(g16, kmap, kernel, role="dgrad_transposed" if transpose else "dgrad")
+            if ctx.needs_input_grad[1]:
+                gw = conv_engine.pairs_wgrad(feats, g16, kmap, kernel.shape[-2], kernel.shape[-1], transpose)
+            return gin, gw, None, None
         if ctx.needs_input_grad[0]:
             if transpose:
                 table, kflip = kmap.nbr, False
@@ -203,6 +238,27 @@ class _SparseConv(torch.autograd.Function):
         return gin, gw, None, None
 
 
+class _DenseConv(torch.autograd.Function):
+    """kernel_size 1 convolution (torchsparse: ``F.matmul(kernel)``) on the same tcgen05 kernels with an identity
+    gather: out = bf16(F) @ bf16(W), fp32 accumulate; dgrad and wgrad likewise."""
+
+    @staticmethod
+    def forward(ctx, feats, kernel):
+        from . import conv_engine
+        x16 = ops.to_bf16(feats.contiguous())
+        ctx.save_for_backward(x16, kernel)
+        return conv_engine.dense_conv(x16, kernel, w_transposed=False)
+
+    @staticmethod
+    def backward(ctx, gout):
+        from . import conv_engine
+        x16, kernel = ctx.saved_tensors
+        g16 = ops.to_bf16(gout.contiguous())
+        gin = conv_engine.dense_conv(g16, kernel, w_transposed=True) if ctx.needs_input_grad[0] else None
+        gw = conv_engine.dense_wgrad(x16, g16, kernel.shape[0], kernel.shape[1]) if ctx.needs_input_grad[1] else None
+        return gin, gw
+
+
 def conv3d(inputs: SparseTensor, kernel: torch.Tensor, kernel_size: int, bias=None, stride: int = 1,
            dilation: int = 1, transpose: bool = False) -> SparseTensor:
     """torchsparse.nn.functional.conv3d v1.1.0; all 49 spnn.Conv3d of models/spvcnn.py."""
@@ -210,7 +266,11 @@ def conv3d(inputs: SparseTensor, kernel: torch.Tensor, kernel_size: int, bias=No
     if dilation != 1:
         raise NotImplementedError("dilation != 1 is never used by the reference (spvcnn.py) and is not implemented")
     if kernel_size == 1 and stride == 1:
-        out = inputs._like(F.matmul(kernel))
+        from . import conv_engine
+        if conv_engine.pairs_ok(kernel.shape[0], kernel.shape[1]):
+            out = inputs._like(_DenseConv.apply(F, kernel))
+        else:
+            out = inputs._like(F.matmul(kernel))
         out.check()
     elif not transpose:
         key = "k%s_os%d_s%d_d%d" % (kernel_size, s, stride, dilation)

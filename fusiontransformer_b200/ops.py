@@ -157,16 +157,25 @@ def kmap_build(coords_q: torch.Tensor, offsets: torch.Tensor, table: CoordTable)
 
 
 def kmap_pairs(nbr: torch.Tensor, k: int):
-    """Reference-format pair list (upper-bound sized) and device-side prefix offsets [K+1]."""
+    """Reference-format pair list (upper-bound sized), device-side prefix offsets [K+1] and the pair-position
+    table ppos [n_out,kpad] (position of pair (row, offset) in the list, -1 if absent)."""
     nbr = _chk(nbr, torch.int32, "nbr")
     n_out, kpad = nbr.shape
     dev = nbr.device
     pairs = torch.empty((max(n_out * k, 1), 2), dtype=torch.int32, device=dev)
     offsets = torch.empty(k + 1, dtype=torch.int32, device=dev)
+    ppos = torch.empty((n_out, kpad), dtype=torch.int32, device=dev)
     ws = _ws(lib().kmap_pairs_workspace(n_out, kpad), dev)
-    lib().kmap_pairs(nbr.data_ptr(), n_out, k, kpad, pairs.data_ptr(), offsets.data_ptr(), ws.data_ptr(),
-                     ws.numel(), _stream())
-    return pairs, offsets
+    lib().kmap_pairs(nbr.data_ptr(), n_out, k, kpad, pairs.data_ptr(), offsets.data_ptr(), ppos.data_ptr(),
+                     ws.data_ptr(), ws.numel(), _stream())
+    return pairs, offsets, ppos
+
+
+def kmap_pair_positions(pairs, offsets, k: int, kpad: int, col: int, n_rows: int, max_pairs: int) -> torch.Tensor:
+    out = torch.empty((n_rows, kpad), dtype=torch.int32, device=pairs.device)
+    lib().kmap_pair_positions(pairs.data_ptr(), offsets.data_ptr(), k, kpad, int(col), n_rows, int(max_pairs),
+                              out.data_ptr(), _stream())
+    return out
 
 
 def kmap_transpose(nbr: torch.Tensor, k: int, n_in: int) -> torch.Tensor:
@@ -361,4 +370,42 @@ def conv_wgrad_tc(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
     gw = torch.zeros((k, cin, cout), dtype=torch.float32, device=a.device)
     lib().conv_wgrad_tc(a.data_ptr(), b.data_ptr(), pairs.data_ptr(), pair_offsets.data_ptr(), k, int(ca), cin,
                         cout, int(max_pairs), gw.data_ptr(), _stream())
+    return gw
+
+
+# ----------------------------------------------------------------------------- pair-major tensor-core path
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    x = _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lib().to_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream())
+    return out
+
+
+def conv_pairs_tc(x16, pairs, offsets, k, gather_col, max_pairs, w, w_transposed, owner=None):
+    """partial[p] = x16[pairs[p][gather_col]] @ (W[k(p)] | W[k(p)]^T) for every pair; identity gather if pairs is None."""
+    x16 = _chk(x16, torch.bfloat16, "x16")
+    cin, cout = w.shape[-2], w.shape[-1]
+    red, ncols = (cout, cin) if w_transposed else (cin, cout)
+    if x16.shape[1] != red:
+        raise Ft3dError("conv: feature width %d != %d" % (x16.shape[1], red))
+    img = packed_weights(w, w_transposed, owner)
+    partial = torch.empty((max(int(max_pairs), 1), ncols), dtype=torch.float32, device=x16.device)
+    lib().conv_pairs_tc(x16.data_ptr(), _p(pairs), _p(offsets), k, int(gather_col), int(max_pairs), red, ncols,
+                        img.data_ptr(), partial.data_ptr(), _stream())
+    return partial
+
+
+def conv_reduce(partial, ppos, k, ncols):
+    n_rows, kpad = ppos.shape
+    out = torch.empty((n_rows, ncols), dtype=torch.float32, device=partial.device)
+    lib().conv_reduce(partial.data_ptr(), ppos.data_ptr(), n_rows, k, kpad, ncols, out.data_ptr(), _stream())
+    return out
+
+
+def conv_wgrad_pairs_tc(a16, b16, pairs, offsets, k, ca, cin, cout, max_pairs):
+    a16 = _chk(a16, torch.bfloat16, "a16")
+    b16 = _chk(b16, torch.bfloat16, "b16")
+    gw = torch.zeros((k, cin, cout), dtype=torch.float32, device=a16.device)
+    lib().conv_wgrad_pairs_tc(a16.data_ptr(), b16.data_ptr(), _p(pairs), _p(offsets), k, int(ca), cin, cout,
+                              int(max_pairs), gw.data_ptr(), _stream())
     return gw

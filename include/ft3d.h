@@ -90,9 +90,15 @@ int ft3d_kmap_build(const int32_t* coords_q, int64_t n_out, const int32_t* offse
  * (in,out), offset-major then out-ascending; offsets_out int32 [K+1] exclusive prefix of the
  * per-offset counts (offsets_out[K] = L).  pairs_out must hold K*n_out rows. */
 size_t ft3d_kmap_pairs_workspace(int64_t n_out, int32_t kpad);
+/* ppos_out (nullable) int32 [n_out,kpad]: position of pair (row j, offset k) in pairs_out, -1 if absent. */
 int ft3d_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad,
-                    int32_t* pairs_out, int32_t* offsets_out, void* workspace,
+                    int32_t* pairs_out, int32_t* offsets_out, int32_t* ppos_out, void* workspace,
                     size_t workspace_bytes, ft3d_stream_t stream);
+/* ppos_out int32 [n_rows,kpad]: ppos_out[pairs[p][col]][k(p)] = p, -1 elsewhere -- the pair-position table seen
+ * from the other side of the map (col 0: input rows, for dgrad and transposed conv; col 1 reproduces the above). */
+int ft3d_kmap_pair_positions(const int32_t* pairs, const int32_t* pair_offsets, int32_t K, int32_t kpad,
+                             int32_t col, int64_t n_rows, int64_t max_pairs, int32_t* ppos_out,
+                             ft3d_stream_t stream);
 /* nbrT_out[i*kpad+k] = j where nbr[j*kpad+k] == i, else -1 (input-stationary view for dgrad and
  * transposed conv, models/spvcnn.py:38-50). */
 int ft3d_kmap_transpose(const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad,
@@ -164,6 +170,26 @@ int ft3d_conv_wgrad_f32(const float* a, const float* b, const int32_t* pairs,
 int ft3d_conv_wgrad_tc(const float* a, const float* b, const int32_t* pairs,
                        const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
                        int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
+
+/* Pair-major tensor-core path (the default): gather -> GEMM -> sorted, atomic-free scatter.
+ *   ft3d_to_bf16        : activations / gradients rounded once to bf16 (dst holds n bf16).
+ *   ft3d_conv_pairs_tc  : partial_out[p,:] = in_bf16[pairs[p][gather_col],:] @ B_k(p)  for every pair p (fp32 rows in
+ *                         pair order; tcgen05.mma, fp32 accumulate in TMEM).  pairs == NULL (with K == 1) is the
+ *                         identity gather over max_pairs rows: a dense GEMM (k = 1 convolutions, torchsparse
+ *                         conv3d kernel_size 1 == F.matmul) whose partial_out IS the result.
+ *   ft3d_conv_reduce    : out[row,:] = sum_k partial[ppos[row,k],:] in ascending k (deterministic, no atomics).
+ *   forward: gather_col 0, ppos of ft3d_kmap_pairs;   dgrad / transposed conv: gather_col 1, ppos of
+ *   ft3d_kmap_pair_positions(col 0) and the w_transposed weight image. */
+int ft3d_to_bf16(const float* src, int64_t n, void* dst, ft3d_stream_t stream);
+int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t* pair_offsets, int32_t K,
+                       int32_t gather_col, int64_t max_pairs, int32_t red, int32_t ncols,
+                       const void* wpacked, float* partial_out, ft3d_stream_t stream);
+int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t K, int32_t kpad,
+                     int32_t ncols, float* out, ft3d_stream_t stream);
+/* wgrad on bf16 inputs: gw[k] += a_bf16[pairs[p][ca],:]^T b_bf16[pairs[p][1-ca],:]; pairs == NULL: identity (K == 1). */
+int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32_t* pairs,
+                             const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin, int32_t cout,
+                             int64_t max_pairs, float* gw, ft3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -216,9 +216,54 @@ def build_kernel_map(coords_in: torch.Tensor, coords_out: torch.Tensor, kernel_s
     return nbr, pairs, counts
 
 
+# Arithmetic mode of the convolution GEMMs.  None = the reference's fp32.  "bf16" restates the product's
+# tensor-core arithmetic (operands rounded to bf16 once, products and sums in fp32) so that bf16-mode parity can be
+# checked to summation-order accuracy instead of through the network's conditioning (DESIGN.md "Tolerances").
+OPERAND_DTYPE = None
+
+
+def _tensor_core_shape(kernel: torch.Tensor) -> bool:
+    """Layers the product runs on tensor cores (fusiontransformer_b200/conv_engine.py::pairs_ok); the others
+    (the 4-channel stem convolution) stay fp32 on both sides."""
+    cin, cout = kernel.shape[-2], kernel.shape[-1]
+    return cin % 32 == 0 and cout % 32 == 0 and cin <= 384 and cout <= 256
+
+
+def _round_operand(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(x.dtype) if OPERAND_DTYPE == "bf16" else x
+
+
+class _RoundedConv(torch.autograd.Function):
+    """sparseconv / matmul with bf16-rounded operands in forward, dgrad and wgrad (fp32 accumulation)."""
+
+    @staticmethod
+    def forward(ctx, fn, feats, kernel):
+        ctx.fn = fn
+        ctx.save_for_backward(feats, kernel)
+        with torch.no_grad():
+            return fn(_round_operand(feats), _round_operand(kernel))
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, kernel = ctx.saved_tensors
+        with torch.enable_grad():
+            f = _round_operand(feats).detach().requires_grad_(True)
+            k = _round_operand(kernel).detach().requires_grad_(True)
+            gf, gk = torch.autograd.grad(ctx.fn(f, k), (f, k), _round_operand(g))
+        return None, gf, gk
+
+
 def sparseconv(feats: torch.Tensor, kernel: torch.Tensor, pairs: torch.Tensor, counts: torch.Tensor,
                sizes, transpose: bool) -> torch.Tensor:
     """Offset-by-offset gather -> mm -> scatter-add (App. A.6 arithmetic), autograd via torch."""
+    if OPERAND_DTYPE is not None and not getattr(sparseconv, "_inner", False) and _tensor_core_shape(kernel):
+        def fn(f, k):
+            sparseconv._inner = True
+            try:
+                return sparseconv(f, k, pairs, counts, sizes, transpose)
+            finally:
+                sparseconv._inner = False
+        return _RoundedConv.apply(fn, feats, kernel)
     n_out = sizes[0] if transpose else sizes[1]
     out = torch.zeros(n_out, kernel.shape[-1], dtype=feats.dtype)
     p = pairs.to(torch.int64)
@@ -272,7 +317,10 @@ def conv3d(inputs: SparseTensor, kernel: torch.Tensor, kernel_size: int, bias=No
     """torchsparse.nn.functional.conv3d (App. A.6); all 49 call sites in spvcnn.py."""
     F, C, s = inputs.F, inputs.C, inputs.s
     if kernel_size == 1 and stride == 1 and dilation == 1:
-        out = SparseTensor(F.matmul(kernel), C, s)
+        if OPERAND_DTYPE is not None and _tensor_core_shape(kernel):
+            out = SparseTensor(_RoundedConv.apply(lambda f, k: f.matmul(k), F, kernel), C, s)
+        else:
+            out = SparseTensor(F.matmul(kernel), C, s)
         out.coord_maps, out.kernel_maps = inputs.coord_maps, inputs.kernel_maps
         out.check()
         return out

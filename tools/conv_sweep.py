@@ -67,10 +67,18 @@ def main():
                 x = torch.randn(cin_c.shape[0], cin, device=dev, generator=g)
                 go = torch.randn(cout_c.shape[0], cout, device=dev, generator=g)
                 w = torch.nn.Parameter(torch.randn(ks ** 3, cin, cout, device=dev, generator=g) * 0.05)
-                t_f = timeit(lambda: conv_engine.gather_conv(x, km.nbr, km, w, False, False))
-                tbl, flip = (km.nbr, True) if km.symmetric else (km.nbrT, False)
-                t_d = timeit(lambda: conv_engine.gather_conv(go, tbl, km, w, flip, True))
-                t_w = timeit(lambda: conv_engine.wgrad(x, go, km, cin, cout, False))
+                if conv_engine.pairs_ok(cin, cout):
+                    from fusiontransformer_b200 import ops
+                    x16, g16 = ops.to_bf16(x), ops.to_bf16(go)
+                    km.ppos, km.pposT
+                    t_f = timeit(lambda: conv_engine.pairs_conv(ops.to_bf16(x), km, w, "forward"))
+                    t_d = timeit(lambda: conv_engine.pairs_conv(ops.to_bf16(go), km, w, "dgrad"))
+                    t_w = timeit(lambda: conv_engine.pairs_wgrad(x16, g16, km, cin, cout, False))
+                else:
+                    t_f = timeit(lambda: conv_engine.gather_conv(x, km.nbr, km, w, False, False))
+                    tbl, flip = (km.nbr, True) if km.symmetric else (km.nbrT, False)
+                    t_d = timeit(lambda: conv_engine.gather_conv(go, tbl, km, w, flip, True))
+                    t_w = timeit(lambda: conv_engine.wgrad(x, go, km, cin, cout, False))
                 fl = 2.0 * L * cin * cout
                 tf = lambda us: fl / (us * 1e-6) / 1e12  # noqa: E731
                 print("%-3d %-6d %-9s %8d %9d | %9.1f %8.2f | %9.1f %8.2f | %9.1f %8.2f" %

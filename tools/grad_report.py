@@ -18,15 +18,16 @@ def main():
     g = torch.Generator().manual_seed(3)
     img = torch.randn(n, 96, generator=g)
     labels = torch.randint(0, 20, (n,), generator=g)
-    torch.manual_seed(1)
-    o = og.Net3DSeg(fusion="middle").train()
-    o.dropout.p = 0.0
-    lo = torch.nn.functional.cross_entropy(o(ts.SparseTensor(feats, coords), img)["lidar_seg_logit"], labels)
-    lo.backward()
-    po = dict(o.named_parameters())
-    gmax = max(p.grad.norm().item() for p in o.parameters() if p.grad is not None)
-    for mode in ("f32", "tc"):
+    for mode, omode in (("f32", None), ("tc", None), ("tc", "bf16")):
         os.environ["FT3D_CONV"] = mode
+        ts.OPERAND_DTYPE = omode
+        torch.manual_seed(1)
+        o = og.Net3DSeg(fusion="middle").train()
+        o.dropout.p = 0.0
+        lo = torch.nn.functional.cross_entropy(o(ts.SparseTensor(feats, coords), img)["lidar_seg_logit"], labels)
+        lo.backward()
+        po = dict(o.named_parameters())
+        gmax = max(p.grad.norm().item() for p in o.parameters() if p.grad is not None)
         m = Net3DSeg(fusion="middle")
         m.load_state_dict(o.state_dict())
         m = m.cuda().train()
@@ -41,7 +42,7 @@ def main():
             d = (p.grad.double().cpu() - go).norm().item()
             rows.append((d / max(go.norm().item(), 1e-4 * gmax), d / max(go.norm().item(), 1e-30), go.norm().item(), name))
         rows.sort(reverse=True)
-        print("mode %s  loss gpu %.6f oracle %.6f  gmax %.3e" % (mode, lg.item(), lo.item(), gmax))
+        print("gpu mode %s vs oracle arithmetic %s:  loss gpu %.6f oracle %.6f  gmax %.3e" % (mode, omode or "fp32", lg.item(), lo.item(), gmax))
         for r in rows[:12]:
             print("   err %.3e  rel %.3e  |g| %.3e  %s" % r)
         med = sorted(r[0] for r in rows)[len(rows) // 2]

@@ -51,8 +51,14 @@ def main():
             step()
         torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / a.steps * 1e3
-    ev = [e for e in prof.key_averages() if e.device_time_total > 0 or getattr(e, "self_device_time_total", 0) > 0]
-    rows = sorted(((e.self_device_time_total / a.steps / 1e3, e.count / a.steps, e.key) for e in ev), reverse=True)
+    from torch.autograd import DeviceType
+    agg = {}
+    for e in prof.events():
+        if e.device_type == DeviceType.CUDA:
+            t = agg.setdefault(e.name, [0.0, 0])
+            t[0] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+            t[1] += 1
+    rows = sorted(((v[0] / a.steps / 1e3, v[1] / a.steps, k) for k, v in agg.items()), reverse=True)
     tot = sum(r[0] for r in rows)
     print("wall ms/step (under profiler) %.2f   GPU kernel ms/step %.2f" % (wall, tot))
     for ms, cnt, key in rows[: a.top]:
