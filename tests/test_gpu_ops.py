@@ -332,7 +332,7 @@ def test_conv_k1_and_ragged_sizes(ft, monkeypatch):
             assert rel_l2(yg.F, yo.F) < tol, (mode, n)
         w1 = torch.randn(64, 32)
         y1 = ft.nn.functional.conv3d(ft.SparseTensor(feats.cuda(), C.cuda(), 1), w1.cuda(), 1)
-        assert rel_l2(y1.F, feats @ w1) < 1e-5
+        assert rel_l2(y1.F, feats @ w1) < tol          # tc mode: bf16 operands on the dense tcgen05 path
 
 
 # ----------------------------------------------------------------------------------------------- lift
