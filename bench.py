@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--fusion", default="middle", choices=["none", "middle", "early"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--diag", action="store_true", help="print host-side enqueue time per phase (stderr)")
+    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
+                    help="build each batch's geometry inside its own step (host reads stall the launch queue)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -199,21 +202,50 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     fmap = torch.randn(B, 96, H, W, device=dev, generator=g)   # stands in for the image branch's output (NCHW, fp32)
 
+    if conv_engine.mode() == "tc":
+        # reduced-precision mode: the point-branch nn.Linear GEMMs (a14, cuBLAS) run on TF32 tensor cores as well
+        torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(1)
     net = Net3DSeg(num_classes=20, dual_head=False, fusion=args.fusion).to(dev).train()
     sync = GradSync(net)
     sync.broadcast_parameters(net)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=5e-4, fused=True)
 
-    def train_step(db):
-        lidar, rc, bidx, labels, _, _ = dataflow.voxelize_batch(db)
-        img = ft.nn.functional.lift(fmap, rc, bidx) if args.fusion != "none" else None
-        out = net(lidar, None if img is None else img.detach())
-        loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], labels)
+    # The geometry of batch i+1 (upload, voxelization, kernel maps: every host read of a data-dependent size) is
+    # built on a high-priority side stream while batch i's convolutions run (fusiontransformer_b200/plan.py).
+    from fusiontransformer_b200.plan import Prefetcher
+    pre = Prefetcher(dev) if args.prefetch else None
+
+    diag = {} if args.diag else None
+
+    def tick(name, t0):
+        if diag is not None:
+            diag[name] = diag.get(name, 0.0) + (time.perf_counter() - t0)
+        return time.perf_counter()
+
+    def train_step(batch, nxt=None):
+        t = time.perf_counter()
+        if pre is None:
+            plan = dataflow.prepare_batch(batch, dev)
+        else:
+            if pre._pending is None:
+                pre.submit(dataflow.prepare_batch, batch, dev)
+            plan = pre.get()
+        t = tick("get_plan", t)
+        ex = plan.extras
+        img = ft.nn.functional.lift(fmap, ex["rc"], ex["bidx"]) if args.fusion != "none" else None
+        out = net(ex["lidar"], None if img is None else img.detach())
+        loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], ex["labels"])
+        t = tick("forward", t)
         sync.zero_grad()
         loss.backward()
+        t = tick("backward", t)
         sync.finish()
         opt.step()
+        t = tick("optimizer", t)
+        if pre is not None and nxt is not None:
+            pre.submit(dataflow.prepare_batch, nxt, dev)
+        tick("prefetch_next", t)
         return loss
 
     def barrier():
@@ -236,23 +268,34 @@ def main():
 
     L = _lib.lib()
     for i in range(args.warmup):
-        train_step(resident[i % nbatches])
+        train_step(resident[i % nbatches], resident[(i + 1) % nbatches])
     # ---- device-resident timing (the `value`)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     L.calls.clear()
-    ms = timed(lambda i: train_step(resident[i % nbatches]), args.steps)
+    ms = timed(lambda i: train_step(resident[i % nbatches], resident[(i + 1) % nbatches]), args.steps)
+    if pre is not None and pre._pending is not None:
+        pre.get()
     launches = _lib.launch_count(L.calls)
+    if diag is not None:
+        print("host enqueue ms/step (device-resident loop): " +
+              ", ".join("%s %.2f" % (k, 1e3 * v / (args.steps + args.warmup)) for k, v in diag.items()), file=sys.stderr)
+        diag.clear()
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end-to-end timing through the public API: pinned host batch -> H2D -> step -> loss to host
     def e2e_step(i):
-        loss = train_step(dataflow.to_device(host[i % nbatches], dev))
+        loss = train_step(host[i % nbatches], host[(i + 1) % nbatches])     # pinned host batches: H2D inside the step
         return loss.item()
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
+    if pre is not None and pre._pending is not None:
+        pre.get()
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    if diag is not None:
+        print("host enqueue ms/step (e2e loop): " +
+              ", ".join("%s %.2f" % (k, 1e3 * v / (args.steps + 2)) for k, v in diag.items()), file=sys.stderr)
     h2d = int(np.mean([h.nbytes() for h in host]))
 
     # ---- per-entry-point device times + conv work log (separate pass, not part of the reported value)
@@ -265,7 +308,7 @@ def main():
         torch.cuda.synchronize()
         e0.record()
         for i in range(nprof):
-            train_step(resident[i % nbatches])
+            train_step(resident[i % nbatches], resident[(i + 1) % nbatches])
         e1.record()
         torch.cuda.synchronize()
         prof, work = L.profile, conv_engine.WORK_LOG
@@ -279,23 +322,36 @@ def main():
         shares = {k: round(v[0] / nprof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])}
         shares["_step_ms_profiled"] = round(step_ms, 3)
         shares["_libft3d_ms"] = round(sum(v[0] for v in tot.values()) / nprof, 3)
-        flops = {}
-        for w in work:
-            f = flops.setdefault(w["kind"], [0.0, 0])
-            f[0] += 2.0 * w["pairs"] * w["red"] * w["ncols"]
-            f[1] += 1
-        kinds = [k for k in ("conv_gather_tc", "conv_wgrad_tc") if k in tot and k in flops]
-        if kinds:
-            dom = max(kinds, key=lambda k: tot[k][0])
-            ach = flops[dom][0] / (tot[dom][0] * 1e-3) / 1e12
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s",
-                        "frac": ach / pk["tf_sus"], "traffic": None,
-                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk["src"] == "measured" else "fallback",
+        # The dominant kernel is the pair-major tcgen05 GEMM (conv_pairs_tc): forward, dgrad, transposed and k=1
+        # convolutions all run through it.  Algorithmic work of one launch (DESIGN.md "Roofline accounting"):
+        #   flops = 2 L red ncols ;  bytes = 2 (rows_in red + K red ncols) + 4 rows_out ncols + 8 L   (SURVEY 8(d), bf16
+        #   operands, fp32 result).  Both bounds are evaluated per launch; the binding one is reported.
+        dom = "conv_pairs_tc"
+        convs = [w for w in work if w["kind"] == dom]
+        if dom in tot and convs:
+            t_s = tot[dom][0] * 1e-3
+            fl = sum(2.0 * w["pairs"] * w["red"] * w["ncols"] for w in convs)
+            by = sum(2.0 * (w["rows_in"] * w["red"] + w["K"] * w["red"] * w["ncols"]) + 4.0 * w["rows"] * w["ncols"]
+                     + 8.0 * w["pairs"] for w in convs)
+            t_tensor, t_hbm = fl / (pk["tf_sus"] * 1e12), by / (pk["hbm"] * 1e9)
+            bound = "tensor" if t_tensor >= t_hbm else "hbm"
+            ach, peak, unit = (fl / t_s / 1e12, pk["tf_sus"], "TFLOP/s") if bound == "tensor" else \
+                              (by / t_s / 1e9, pk["hbm"], "GB/s")
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "traffic_conv_pairs_tc.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "traffic": traffic,
+                        "peak_source": ("MEASURED_PEAKS.json (hbm_gbs / bf16_tflops_sustained)" if pk["src"] == "measured"
+                                        else "fallback of B200_PROFILING.md"),
                         "launches_per_step": tot[dom][1] / nprof, "avg_launch_us": 1e3 * tot[dom][0] / tot[dom][1],
-                        "algorithmic_gflop_per_launch": flops[dom][0] / flops[dom][1] / 1e9,
+                        "algorithmic_mb_per_launch": by / len(convs) / 1e6,
+                        "algorithmic_gflop_per_launch": fl / len(convs) / 1e9,
+                        "tflops": fl / t_s / 1e12, "gbs": by / t_s / 1e9,
                         "share_of_step": tot[dom][0] / nprof / step_ms,
-                        "others": {k: {"tflops": flops[k][0] / (tot[k][0] * 1e-3) / 1e12, "ms_per_step": tot[k][0] / nprof}
-                                   for k in kinds if k != dom}}
+                        "note": "time = CUDA events around every conv_pairs_tc launch on the launching stream, "
+                                "summed over %d profiled steps" % nprof}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -312,6 +368,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if conv_engine.mode() == "tc" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "scans_per_gpu": B, "points_per_batch": nvox, "fusion": args.fusion,
                        "image_hw": [H, W], "parallelism": "dp%d" % world, "optimizer": "Adam(lr 1e-4, wd 5e-4)",
+                       "geometry_prefetch": bool(args.prefetch),
+                       "linear_layers": "cuBLAS TF32" if conv_engine.mode() == "tc" else "cuBLAS fp32",
                        "l2": "no explicit flush: %d distinct batches are cycled and the step's working set (348 MB of "
                              "weights+Adam state, the activations and the %.1f GB feature map) exceeds the 126 MB L2"
                              % (nbatches, B * 96 * H * W * 4 / 1e9)},

@@ -26,13 +26,19 @@ from . import functional, nn, utils  # noqa: F401
 nn.functional = functional
 sys.modules[__name__ + ".nn.functional"] = functional
 
-__all__ = ["SparseTensor", "PointTensor", "cat", "nn", "utils", "install_as_torchsparse"]
+from .fused import fuse, unfuse  # noqa: E402
+
+__all__ = ["SparseTensor", "PointTensor", "cat", "nn", "utils", "install_as_torchsparse", "fuse", "unfuse"]
 __version__ = "0.1.0"
 
 
 def cat(input_list, dim=1):
     """torchsparse.cat (spvcnn.py:212,216,224,228): concatenate features, keep the first tensor's coords/maps."""
-    return input_list[0]._like(torch.cat([t.F for t in input_list], dim))
+    out = input_list[0]._like(torch.cat([t.F for t in input_list], dim))
+    f16 = [getattr(t, "F16", None) for t in input_list]
+    if dim == 1 and all(h is not None for h in f16):
+        out.F16 = torch.cat(f16, 1)        # keep the tensor-core operand copy alive across the skip concatenation
+    return out
 
 
 def install_as_torchsparse():

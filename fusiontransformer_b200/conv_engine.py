@@ -15,8 +15,15 @@ import torch
 from . import ops
 
 
+_environ = os.environ          # os.environ.get() encodes/decodes on every call; the raw mapping lookup is 10x cheaper
+_KEY_CONV, _KEY_ALGO = os.environ.encodekey("FT3D_CONV"), os.environ.encodekey("FT3D_CONV_ALGO")
+
+
 def mode() -> str:
-    m = os.environ.get("FT3D_CONV", "tc")
+    m = _environ._data.get(_KEY_CONV)
+    if m is None:
+        return "tc"
+    m = os.environ.decodevalue(m)
     if m not in ("tc", "f32"):
         raise ValueError("FT3D_CONV must be 'tc' or 'f32'")
     return m
@@ -64,12 +71,14 @@ def pairs_ok(cin: int, cout: int) -> bool:
     """Both the forward (red=cin, ncols=cout), the dgrad (red=cout, ncols=cin) and the wgrad shape must be covered."""
     def gemm_ok(red, ncols):
         return red % 16 == 0 and 16 <= red <= 512 and ncols % 32 == 0 and (32 <= ncols <= 256 or ncols == 384)
-    return (mode() == "tc" and os.environ.get("FT3D_CONV_ALGO", "pairs") == "pairs" and gemm_ok(cin, cout)
+    algo = _environ._data.get(_KEY_ALGO)
+    return (mode() == "tc" and (algo is None or os.environ.decodevalue(algo) == "pairs") and gemm_ok(cin, cout)
             and gemm_ok(cout, cin) and cout <= 256)
 
 
-def pairs_conv(x16, kmap, kernel, role: str):
-    """role: forward | dgrad | transposed | dgrad_transposed (which side of the map is gathered / scattered)."""
+def pairs_partial(x16, kmap, kernel, role: str):
+    """Pair-major GEMM of one conv: returns (partial rows [L,ncols] f32, the pair-position table that scatters them).
+    role: forward | dgrad | transposed | dgrad_transposed (which side of the map is gathered / scattered)."""
     w = kernel.detach()
     K, L = kmap.K, kmap.num_pairs()
     pairs, offsets = kmap.pairs_padded, kmap.pair_offsets
@@ -86,17 +95,22 @@ def pairs_conv(x16, kmap, kernel, role: str):
         raise ValueError(role)
     red = cout if wt else cin
     if WORK_LOG is not None:
-        WORK_LOG.append(dict(kind="conv_pairs_tc", pairs=L, red=red, ncols=ncols, rows=ppos.shape[0], K=K))
-    partial = ops.conv_pairs_tc(x16, pairs, offsets, K, gcol, L, w, wt, owner=kernel)
-    return ops.conv_reduce(partial, ppos, K, ncols)
+        WORK_LOG.append(dict(kind="conv_pairs_tc", pairs=L, red=red, ncols=ncols, rows=ppos.shape[0], K=K,
+                             rows_in=x16.shape[0]))
+    return ops.conv_pairs_tc(x16, pairs, offsets, K, gcol, L, w, wt, owner=kernel), ppos, ncols
 
 
-def pairs_wgrad(x16, g16, kmap, cin: int, cout: int, transpose: bool):
+def pairs_conv(x16, kmap, kernel, role: str):
+    partial, ppos, ncols = pairs_partial(x16, kmap, kernel, role)
+    return ops.conv_reduce(partial, ppos, ncols)
+
+
+def pairs_wgrad(x16, g16, kmap, cin: int, cout: int, transpose: bool, into=None):
     L = kmap.num_pairs()
     if WORK_LOG is not None:
         WORK_LOG.append(dict(kind="conv_wgrad_pairs_tc", pairs=L, red=cin, ncols=cout, rows=L, K=kmap.K))
     return ops.conv_wgrad_pairs_tc(x16, g16, kmap.pairs_padded, kmap.pair_offsets, kmap.K, 1 if transpose else 0,
-                                   cin, cout, L)
+                                   cin, cout, L, into=into)
 
 
 def dense_conv(x16, kernel, w_transposed: bool):
@@ -104,12 +118,12 @@ def dense_conv(x16, kernel, w_transposed: bool):
     n = x16.shape[0]
     if WORK_LOG is not None:
         WORK_LOG.append(dict(kind="conv_pairs_tc", pairs=n, red=x16.shape[1],
-                             ncols=w.shape[1] if w_transposed else w.shape[2], rows=n, K=1))
+                             ncols=w.shape[1] if w_transposed else w.shape[2], rows=n, K=1, rows_in=n))
     return ops.conv_pairs_tc(x16, None, None, 1, 0, n, w, w_transposed, owner=kernel)[:n]
 
 
-def dense_wgrad(x16, g16, cin: int, cout: int):
+def dense_wgrad(x16, g16, cin: int, cout: int, into=None):
     n = x16.shape[0]
     if WORK_LOG is not None:
         WORK_LOG.append(dict(kind="conv_wgrad_pairs_tc", pairs=n, red=cin, ncols=cout, rows=n, K=1))
-    return ops.conv_wgrad_pairs_tc(x16, g16, None, None, 1, 0, cin, cout, n).view(cin, cout)
+    return ops.conv_wgrad_pairs_tc(x16, g16, None, None, 1, 0, cin, cout, n, into=into).view(cin, cout)

@@ -1,0 +1,215 @@
+// spnn.BatchNorm + spnn.ReLU + residual add fused around the sparse convolution (a11; models/spvcnn.py:26-31,57-78).
+//
+// The reference runs conv -> BatchNorm1d -> ReLU (-> add -> ReLU) as separate ATen kernels: three or more full
+// read+write passes over every activation plus a separate fp32->bf16 pass for the next convolution's operands.
+// Here:
+//   forward   statistics are produced by the convolution's sorted scatter (conv_pairs_tc.cu) or by bn_stats_kernel;
+//             bn_apply_kernel then makes ONE pass: normalise, affine, (+ residual), (ReLU), and writes the fp32
+//             activation and the bf16 copy the next convolution gathers from.
+//   backward  bn_bwd_reduce_kernel (one pass: ReLU mask, sum g, sum g*xhat -> dgamma, dbeta) and bn_bwd_apply_kernel
+//             (one pass: dx, written as the bf16 operand of dgrad/wgrad, plus the masked gradient of the residual).
+// All are HBM-bound streaming kernels: float4 per thread, channel-fastest so a warp touches contiguous 512 B.
+#include "bn_common.cuh"
+#include "tc_common.cuh"
+
+namespace ft3d {
+
+using tc::pack_bf16x2;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
+  float4 f;
+  f.x = __uint_as_float(v.x << 16);
+  f.y = __uint_as_float(v.x & 0xFFFF0000u);
+  f.z = __uint_as_float(v.y << 16);
+  f.w = __uint_as_float(v.y & 0xFFFF0000u);
+  return f;
+}
+
+// ------------------------------------------------------------------------------------------------ statistics
+__global__ void __launch_bounds__(kColThreads)
+bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_per_cta,
+                float* __restrict__ partials) {
+  __shared__ float4 s_stage[kColStageFloat4];
+  const int ch = threadIdx.x * 4;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  for (int64_t r = row0 + threadIdx.y; r < row1; r += blockDim.y) {
+    const float4 v = ld4(y + r * channels + ch);
+    add4(s1, v);
+    fma4(s2, v, v);
+  }
+  col_publish(s1, s2, partials, channels, s_stage);
+}
+
+// ------------------------------------------------------------------------------------------------ forward apply
+// z = [relu]( (y - mean) * rstd * gamma + beta [+ res] );  writes z (fp32, nullable) and z16 (bf16, nullable).
+__global__ void bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, const float* __restrict__ stat,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ res, int relu, float* __restrict__ z,
+                                __nv_bfloat16* __restrict__ z16) {
+  const int cv = channels >> 2;
+  const int64_t total = n * cv;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / cv;
+    const int ch = (int)(t - row * cv) << 2;
+    const float4 v = ld4(y + row * channels + ch);
+    const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), g = ld4(gamma + ch), b = ld4(beta + ch);
+    float4 o;
+    o.x = fmaf((v.x - m.x) * rs.x, g.x, b.x);
+    o.y = fmaf((v.y - m.y) * rs.y, g.y, b.y);
+    o.z = fmaf((v.z - m.z) * rs.z, g.z, b.z);
+    o.w = fmaf((v.w - m.w) * rs.w, g.w, b.w);
+    if (res != nullptr) add4(o, ld4(res + row * channels + ch));
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    if (z != nullptr) *reinterpret_cast<float4*>(z + row * channels + ch) = o;
+    if (z16 != nullptr)
+      *reinterpret_cast<uint2*>(z16 + row * channels + ch) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// g' = gz * [z > 0]   (mask from the saved output: bf16 copy if present, else fp32; no mask when both are null)
+__device__ __forceinline__ float4 masked_grad(const float* __restrict__ gz, const __nv_bfloat16* __restrict__ z16,
+                                              const float* __restrict__ z, int64_t off) {
+  float4 g = ld4(gz + off);
+  if (z16 != nullptr) {
+    const float4 o = bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(z16 + off)));
+    g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+  } else if (z != nullptr) {
+    const float4 o = ld4(z + off);
+    g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+  }
+  return g;
+}
+
+// red = [c1[C], c2[C]] = [sum g'/n, sum g'*xhat/n];  dgamma = sum g'*xhat;  dbeta = sum g'
+__global__ void __launch_bounds__(kColThreads)
+bn_bwd_reduce_kernel(const float* __restrict__ gz, const float* __restrict__ y, const __nv_bfloat16* __restrict__ z16,
+                     const float* __restrict__ z, int64_t n, int channels, int rows_per_cta,
+                     const float* __restrict__ stat, float* __restrict__ partials) {
+  __shared__ float4 s_stage[kColStageFloat4];
+  const int ch = threadIdx.x * 4;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
+  const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  for (int64_t r = row0 + threadIdx.y; r < row1; r += blockDim.y) {
+    const int64_t off = r * channels + ch;
+    const float4 g = masked_grad(gz, z16, z, off);
+    const float4 v = ld4(y + off);
+    const float4 xh = make_float4((v.x - m.x) * rs.x, (v.y - m.y) * rs.y, (v.z - m.z) * rs.z, (v.w - m.w) * rs.w);
+    add4(s1, g);
+    fma4(s2, g, xh);
+  }
+  col_publish(s1, s2, partials, channels, s_stage);
+}
+
+// gy = gamma * rstd * (g' - c1 - xhat * c2)   (training);   gy = gamma * rstd * g'   (frozen statistics: red == null)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ gz, const float* __restrict__ y,
+                                    const __nv_bfloat16* __restrict__ z16, const float* __restrict__ z, int64_t n,
+                                    int channels, const float* __restrict__ stat, const float* __restrict__ gamma,
+                                    const float* __restrict__ red, float* __restrict__ gy,
+                                    __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres) {
+  const int cv = channels >> 2;
+  const int64_t total = n * cv;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / cv;
+    const int ch = (int)(t - row * cv) << 2;
+    const int64_t off = row * channels + ch;
+    const float4 g = masked_grad(gz, z16, z, off);
+    const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), ga = ld4(gamma + ch);
+    float4 o;
+    if (red != nullptr) {
+      const float4 v = ld4(y + off);
+      const float4 c1 = ld4(red + ch), c2 = ld4(red + channels + ch);
+      o.x = ga.x * rs.x * (g.x - c1.x - (v.x - m.x) * rs.x * c2.x);
+      o.y = ga.y * rs.y * (g.y - c1.y - (v.y - m.y) * rs.y * c2.y);
+      o.z = ga.z * rs.z * (g.z - c1.z - (v.z - m.z) * rs.z * c2.z);
+      o.w = ga.w * rs.w * (g.w - c1.w - (v.w - m.w) * rs.w * c2.w);
+    } else {
+      o = make_float4(ga.x * rs.x * g.x, ga.y * rs.y * g.y, ga.z * rs.z * g.z, ga.w * rs.w * g.w);
+    }
+    if (gy != nullptr) *reinterpret_cast<float4*>(gy + off) = o;
+    if (gy16 != nullptr) *reinterpret_cast<uint2*>(gy16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    if (gres != nullptr) *reinterpret_cast<float4*>(gres + off) = g;
+  }
+}
+
+}  // namespace ft3d
+
+using namespace ft3d;
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" {
+
+size_t ft3d_bn_workspace(int32_t channels) { return col_workspace_bytes(channels > 0 ? channels : 4); }
+
+int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float momentum, float* stat,
+                  float* running_mean, float* running_var, void* workspace, size_t workspace_bytes,
+                  ft3d_stream_t stream) {
+  FT3D_REQUIRE(n > 0, "ft3d_bn_stats: BatchNorm statistics need at least one row");
+  FT3D_REQUIRE(y && stat && workspace && channels >= 4 && channels % 4 == 0 && channels <= 1024,
+               "ft3d_bn_stats: bad arguments (channels=%d)", channels);
+  FT3D_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "ft3d_bn_stats: running stats go together");
+  FT3D_REQUIRE(aligned16(y) && aligned16(workspace), "ft3d_bn_stats: pointers must be 16-byte aligned");
+  FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_stats: workspace too small");
+  ColGrid g = col_grid(n, channels / 4);
+  bn_stats_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>(y, n, channels, g.rows_per_cta, (float*)workspace);
+  col_finalize_kernel<0><<<channels / 4, kColThreads, 0, (cudaStream_t)stream>>>(
+      (const float*)workspace, g.grid, channels, n, eps, momentum, stat, running_mean, running_var, 0);
+  return check_launch("ft3d_bn_stats");
+}
+
+int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma, const float* beta,
+                  const float* res, int32_t relu, float* z, void* z16, ft3d_stream_t stream) {
+  if (n == 0) return FT3D_OK;
+  FT3D_REQUIRE(y && stat && gamma && beta && (z || z16) && channels >= 4 && channels % 4 == 0,
+               "ft3d_bn_apply: bad arguments");
+  FT3D_REQUIRE(aligned16(y) && aligned16(stat) && aligned16(gamma) && aligned16(beta) && aligned16(res) &&
+                   aligned16(z) && ((uintptr_t)z16 & 7) == 0,
+               "ft3d_bn_apply: pointers must be 16-byte aligned");
+  bn_apply_kernel<<<grid_for(n * (channels / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      y, n, channels, stat, gamma, beta, res, relu, z, (__nv_bfloat16*)z16);
+  return check_launch("ft3d_bn_apply");
+}
+
+int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const float* z, int64_t n, int32_t channels,
+                       const float* stat, float* red, float* dgamma, float* dbeta, int32_t accumulate,
+                       void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
+  FT3D_REQUIRE(n > 0, "ft3d_bn_bwd_reduce: needs at least one row");
+  FT3D_REQUIRE(gz && y && stat && red && dgamma && dbeta && workspace && channels >= 4 &&
+                   channels % 4 == 0 && channels <= 1024,
+               "ft3d_bn_bwd_reduce: bad arguments");
+  FT3D_REQUIRE(aligned16(gz) && aligned16(y) && aligned16(z) && ((uintptr_t)z16 & 7) == 0 && aligned16(stat) &&
+                   aligned16(workspace),
+               "ft3d_bn_bwd_reduce: pointers must be 16-byte aligned");
+  FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_bwd_reduce: workspace too small");
+  ColGrid g = col_grid(n, channels / 4);
+  bn_bwd_reduce_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>(
+      gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace);
+  col_finalize_kernel<1><<<channels / 4, kColThreads, 0, (cudaStream_t)stream>>>(
+      (const float*)workspace, g.grid, channels, n, 0.f, 0.f, red, dgamma, dbeta, accumulate);
+  return check_launch("ft3d_bn_bwd_reduce");
+}
+
+int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const float* z, int64_t n, int32_t channels,
+                      const float* stat, const float* gamma, const float* red, float* gy, void* gy16, float* gres,
+                      ft3d_stream_t stream) {
+  if (n == 0) return FT3D_OK;
+  FT3D_REQUIRE(gz && stat && gamma && (y || !red) && (gy || gy16 || gres) && channels >= 4 && channels % 4 == 0,
+               "ft3d_bn_bwd_apply: bad arguments");
+  FT3D_REQUIRE(aligned16(gz) && aligned16(y) && aligned16(z) && ((uintptr_t)z16 & 7) == 0 && aligned16(stat) &&
+                   aligned16(gamma) && aligned16(red) && aligned16(gy) && ((uintptr_t)gy16 & 7) == 0 && aligned16(gres),
+               "ft3d_bn_bwd_apply: pointers must be 16-byte aligned");
+  bn_bwd_apply_kernel<<<grid_for(n * (channels / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      gz, y, (const __nv_bfloat16*)z16, z, n, channels, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres);
+  return check_launch("ft3d_bn_bwd_apply");
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Per-channel column reductions shared by the BatchNorm kernels and the convolution's sorted scatter.
+//
+// Every kernel that reduces over rows uses a 2-D thread block: threadIdx.x = one group of 4 channels (a float4 of a
+// row), threadIdx.y = row lane.  A thread keeps its channels for its whole life, accumulates its rows in registers,
+// the block folds the row lanes in shared memory and writes ONE partial row per CTA to `partials`; a second, tiny
+// launch folds the partial rows in double precision with a fixed-shape tree.  No float atomics: the result is
+// independent of scheduling (deterministic), as the reference's cuDNN/ATen batch-norm reductions are.
+#pragma once
+#include "common.cuh"
+
+namespace ft3d {
+
+constexpr int kColMaxCtas = kNumSMs * 8;        // upper bound on CTAs of a column-reduction launch
+constexpr int kColThreads = 256;                // target threads per CTA
+constexpr int kColStageFloat4 = kColThreads * 2; // __shared__ float4 staging every column-reduction kernel declares
+
+struct ColGrid {
+  dim3 block;
+  int grid;
+  int rows_per_cta;
+};
+
+// cv = channels / 4.  Rows are split into contiguous per-CTA chunks (multiples of the row-lane count).
+static inline ColGrid col_grid(int64_t n_rows, int cv) {
+  ColGrid g;
+  int ry = kColThreads / cv;
+  if (ry < 1) ry = 1;
+  if (ry > 32) ry = 32;
+  g.block = dim3((unsigned)cv, (unsigned)ry, 1);
+  int64_t want = (n_rows + ry - 1) / ry;                 // CTAs if each did one row per lane
+  int64_t ctas = want < kColMaxCtas ? want : kColMaxCtas;
+  if (ctas < 1) ctas = 1;
+  int64_t rpc = (n_rows + ctas - 1) / ctas;
+  rpc = (rpc + ry - 1) / ry * ry;
+  if (rpc < ry) rpc = ry;
+  g.rows_per_cta = (int)rpc;
+  g.grid = (int)((n_rows + rpc - 1) / rpc);
+  if (g.grid < 1) g.grid = 1;
+  return g;
+}
+
+static inline size_t col_workspace_bytes(int channels) {
+  return align_up((size_t)kColMaxCtas * 2 * channels * sizeof(float), 256);
+}
+
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void fma4(float4& a, const float4& b, const float4& c) {
+  a.x = fmaf(b.x, c.x, a.x); a.y = fmaf(b.y, c.y, a.y); a.z = fmaf(b.z, c.z, a.z); a.w = fmaf(b.w, c.w, a.w);
+}
+
+// Fold (s1, s2) over the row lanes of the CTA and publish the CTA's partial row: partials[cta][0][C], [cta][1][C].
+// `s_stage` must hold 2 * blockDim.x * blockDim.y float4.
+__device__ __forceinline__ void col_publish(float4 s1, float4 s2, float* __restrict__ partials, int channels,
+                                            float4* s_stage) {
+  const int cv = blockDim.x, ry = blockDim.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  s_stage[(ty * cv + tx) * 2] = s1;
+  s_stage[(ty * cv + tx) * 2 + 1] = s2;
+  __syncthreads();
+  if (ty == 0) {
+    for (int r = 1; r < ry; ++r) {
+      add4(s1, s_stage[(r * cv + tx) * 2]);
+      add4(s2, s_stage[(r * cv + tx) * 2 + 1]);
+    }
+    float* p = partials + (size_t)blockIdx.x * 2 * channels;
+    *reinterpret_cast<float4*>(p + tx * 4) = s1;
+    *reinterpret_cast<float4*>(p + channels + tx * 4) = s2;
+  }
+}
+
+// Second stage (its own tiny launch, stream-ordered after the main kernel): CTA g owns channels 4g..4g+3, its 256
+// threads read the partial rows in parallel (one L2 round trip instead of a serial walk by a "last CTA"), accumulate
+// in double and fold with a fixed-shape tree -> the summation order depends only on (nparts, blockDim).
+//   MODE 0: BatchNorm training statistics (torch.nn.BatchNorm1d semantics: biased variance for the normalisation,
+//           unbiased for running_var); out0 = stat [2,C] = (mean, rstd).
+//   MODE 1: BatchNorm backward sums; out0 = red [2,C] = (sum g/n, sum g*xhat/n), out1 = dgamma, out2 = dbeta
+//           (`accumulate`: added to what out1/out2 hold -- gradients written straight into the optimizer's arena).
+template <int MODE>
+__global__ void __launch_bounds__(kColThreads)
+col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels, int64_t n, float eps, float momentum,
+                    float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2, int accumulate) {
+  __shared__ double s_acc[kColThreads][8];
+  const int t = threadIdx.x, c0 = blockIdx.x * 4;
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = t; b < nparts; b += kColThreads) {
+    const float* p = partials + (size_t)b * 2 * channels + c0;
+    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + channels));
+    a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+    a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_acc[t][e] = a[e];
+  __syncthreads();
+  for (int stride = kColThreads / 2; stride >= 1; stride >>= 1) {
+    if (t < stride) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_acc[t][e] += s_acc[t + stride][e];
+    }
+    __syncthreads();
+  }
+  if (t < 4) {
+    const int c = c0 + t;
+    const double s1 = s_acc[0][t], s2 = s_acc[0][4 + t];
+    if (MODE == 0) {
+      const double mean = s1 / (double)n;
+      double var = s2 / (double)n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      out0[c] = (float)mean;
+      out0[channels + c] = (float)(1.0 / sqrt(var + (double)eps));
+      if (out1 != nullptr) {             // running_mean / running_var
+        const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+        out1[c] = (float)((1.0 - momentum) * (double)out1[c] + (double)momentum * mean);
+        out2[c] = (float)((1.0 - momentum) * (double)out2[c] + (double)momentum * unbiased);
+      }
+    } else {
+      out0[c] = (float)(s1 / (double)n);
+      out0[channels + c] = (float)(s2 / (double)n);
+      out1[c] = (float)s2 + (accumulate ? out1[c] : 0.f);   // dgamma
+      out2[c] = (float)s1 + (accumulate ? out2[c] : 0.f);   // dbeta
+    }
+  }
+}
+
+}  // namespace ft3d

@@ -17,6 +17,7 @@
 // The same kernel runs dense GEMMs (k = 1 convolutions) with an identity gather (pairs == nullptr).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "bn_common.cuh"
 
 namespace ft3d {
 using namespace tc;
@@ -30,6 +31,7 @@ struct PairsSmemHeader {
   uint64_t empty[kPMaxStages];
   uint64_t accum_full;
   uint32_t tmem_base;
+  int32_t off[40];          // the map's K+1 prefix offsets
   int32_t idx[kTileRows];
 };
 
@@ -40,12 +42,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// tile -> (offset k, [begin,end) in the pair list); tiles never straddle offsets
-__device__ __forceinline__ bool pair_tile(const int32_t* __restrict__ off, int K, int item, int rows, int* k_out,
+// tile -> (offset k, [begin,end) in the pair list); tiles never straddle offsets.  `off` is the CTA's shared-memory
+// copy of the K+1 prefix offsets (one L2 round trip for the whole CTA instead of one per scanned offset).
+__device__ __forceinline__ bool pair_tile(const int32_t* off, int K, int item, int rows, int* k_out,
                                           int* begin, int* end) {
   int acc = 0;
   for (int k = 0; k < K; ++k) {
-    int b = __ldg(off + k), e = __ldg(off + k + 1);
+    int b = off[k], e = off[k + 1];
     int nt = (e - b + rows - 1) / rows;
     if (item < acc + nt) {
       *k_out = k;
@@ -85,7 +88,9 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
 
   int k = 0, begin, end;
   if (pairs != nullptr) {
-    if (!pair_tile(off, K, blockIdx.x, kTileRows, &k, &begin, &end)) return;   // uniform per CTA
+    if ((int)threadIdx.x <= K) hdr->off[threadIdx.x] = __ldg(off + threadIdx.x);
+    __syncthreads();
+    if (!pair_tile(hdr->off, K, blockIdx.x, kTileRows, &k, &begin, &end)) return;   // uniform per CTA
   } else {
     begin = blockIdx.x * kTileRows;
     end = (int)min((int64_t)begin + kTileRows, n_identity);
@@ -185,36 +190,75 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ sorted scatter
-// out[row,:] = sum over k (ascending) of P[ppos[row,k],:]  -- one thread per (row, 4 channels)
-__global__ void conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos, int64_t n_rows, int K,
-                                   int kpad, int ncols, float* __restrict__ out) {
-  const int cv = ncols >> 2;
-  const int64_t total = n_rows * cv;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = t / cv;
-    const int ch = (int)(t - row * cv) << 2;
+// out[row,:] = sum of P[ppos[row,j],:] over the row's pair positions (stored compacted in ascending offset order and
+// terminated by -1).  2-D block: threadIdx.x = 4 channels, threadIdx.y = row lane; each CTA owns a contiguous chunk
+// of rows.  With STATS the per-channel sum / sum of squares of the rows just written are folded per CTA and a tiny
+// second launch turns them into the BatchNorm statistics of this layer (bn_common.cuh): the activation is not re-read.
+template <bool STATS>
+__global__ void __launch_bounds__(kColThreads)
+conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos, int64_t n_rows, int kpad, int ncols,
+                   int rows_per_cta, float* __restrict__ out, float* __restrict__ partials) {
+  __shared__ float4 s_stage[STATS ? kColStageFloat4 : 1];
+  const int ch = threadIdx.x * 4;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t row1 = row0 + rows_per_cta < n_rows ? row0 + rows_per_cta : n_rows;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const int nq = kpad >> 2;
+  for (int64_t row = row0 + threadIdx.y; row < row1; row += blockDim.y) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int32_t* pr = ppos + row * kpad;
-    for (int k = 0; k < K; ++k) {
-      const int p = __ldg(pr + k);
-      if (p >= 0) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(P + (int64_t)p * ncols + ch));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
+    const int4* pr = reinterpret_cast<const int4*>(ppos + row * kpad);
+    for (int q = 0; q < nq; ++q) {
+      const int4 pp = __ldg(pr + q);
+      if (pp.x < 0) break;
+      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.x * ncols + ch)));
+      if (pp.y < 0) break;
+      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.y * ncols + ch)));
+      if (pp.z < 0) break;
+      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.z * ncols + ch)));
+      if (pp.w < 0) break;
+      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.w * ncols + ch)));
     }
     *reinterpret_cast<float4*>(out + row * ncols + ch) = acc;
+    if (STATS) {
+      add4(s1, acc);
+      fma4(s2, acc, acc);
+    }
   }
+  if (STATS) col_publish(s1, s2, partials, ncols, s_stage);
 }
 
 // pposT[gather-side row][k] = pair position, for the role-swapped use of a map (dgrad, transposed conv)
 __global__ void pair_positions_kernel(const int2* __restrict__ pairs, const int32_t* __restrict__ off, int K, int kpad,
                                       int col, int32_t* __restrict__ ppos) {
-  const int total = __ldg(off + K);
+  __shared__ int32_t s_off[40];
+  if ((int)threadIdx.x <= K) s_off[threadIdx.x] = __ldg(off + threadIdx.x);
+  __syncthreads();
+  const int total = s_off[K];
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
     int k = 0;
-    while (k + 1 < K && p >= __ldg(off + k + 1)) ++k;
+    while (k + 1 < K && p >= s_off[k + 1]) ++k;
     const int2 pr = __ldg(pairs + p);
     ppos[(int64_t)(col ? pr.y : pr.x) * kpad + k] = p;
+  }
+}
+
+// in-place row compaction: valid positions to the front (ascending offset order kept), -1 behind
+__global__ void compact_rows_kernel(int32_t* ppos, int64_t n_rows, int kpad) {
+  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n_rows; row += (int64_t)gridDim.x * blockDim.x) {
+    int4* pr = reinterpret_cast<int4*>(ppos + row * kpad);
+    int v[32];
+    const int nq = kpad >> 2;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int4 t = q < nq ? pr[q] : make_int4(-1, -1, -1, -1);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    int32_t* dst = ppos + row * kpad;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (v[k] >= 0) dst[cnt++] = v[k];
+    for (int j = cnt; j < kpad; ++j) dst[j] = -1;
   }
 }
 
@@ -245,6 +289,7 @@ struct WgSmemHeader {
   uint64_t full[kWgStages];
   uint64_t accum_full;
   uint32_t tmem_base;
+  int32_t off[40];
   int32_t pa[kWgStages][kTileRows];
   int32_t pb[kWgStages][kTileRows];
 };
@@ -263,7 +308,9 @@ conv_wgrad_pairs_tc_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
 
   int k = 0, begin, end;
   if (pairs != nullptr) {
-    if (!pair_tile(off, K, blockIdx.x, rows_per_cta, &k, &begin, &end)) return;
+    if ((int)threadIdx.x <= K) hdr->off[threadIdx.x] = __ldg(off + threadIdx.x);
+    __syncthreads();
+    if (!pair_tile(hdr->off, K, blockIdx.x, rows_per_cta, &k, &begin, &end)) return;
   } else {
     begin = blockIdx.x * rows_per_cta;
     end = (int)min((int64_t)begin + rows_per_cta, n_identity);
@@ -384,6 +431,7 @@ int ft3d_kmap_pair_positions(const int32_t* pairs, const int32_t* pair_offsets, 
     FT3D_REQUIRE(pairs && pair_offsets, "ft3d_kmap_pair_positions: null input");
     pair_positions_kernel<<<grid_for(max_pairs, 256), 256, 0, s>>>((const int2*)pairs, pair_offsets, K, kpad, col,
                                                                    ppos_out);
+    compact_rows_kernel<<<grid_for(n_rows, 128), 128, 0, s>>>(ppos_out, n_rows, kpad);
   }
   return check_launch("ft3d_kmap_pair_positions");
 }
@@ -419,14 +467,42 @@ int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t*
   return check_launch("ft3d_conv_pairs_tc");
 }
 
-int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t K, int32_t kpad,
-                     int32_t ncols, float* out, ft3d_stream_t stream) {
+static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
+                         float* out, bool stats, float eps, float momentum, float* stat, float* running_mean,
+                         float* running_var, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                         const char* what) {
+  FT3D_REQUIRE(ppos && out && (kpad == 8 || kpad == 16 || kpad == 32) && ncols >= 4 && ncols % 4 == 0 && ncols <= 1024,
+               "%s: bad arguments", what);
+  FT3D_REQUIRE(((uintptr_t)partial & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)ppos & 15) == 0,
+               "%s: pointers must be 16-byte aligned", what);
+  ColGrid g = col_grid(n_rows, ncols / 4);
+  if (stats) {
+    FT3D_REQUIRE(stat && workspace && ((uintptr_t)workspace & 15) == 0 &&
+                     workspace_bytes >= col_workspace_bytes(ncols) && (running_mean == nullptr) == (running_var == nullptr),
+                 "%s: statistics need stat and a workspace of ft3d_bn_workspace(ncols) bytes", what);
+    conv_reduce_kernel<true><<<g.grid, g.block, 0, s>>>(partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
+                                                        (float*)workspace);
+    col_finalize_kernel<0><<<ncols / 4, kColThreads, 0, s>>>((const float*)workspace, g.grid, ncols, n_rows, eps, momentum,
+                                                             stat, running_mean, running_var, 0);
+  } else {
+    conv_reduce_kernel<false><<<g.grid, g.block, 0, s>>>(partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr);
+  }
+  return check_launch(what);
+}
+
+int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
+                     float* out, ft3d_stream_t stream) {
   if (n_rows == 0) return FT3D_OK;
-  FT3D_REQUIRE(ppos && out && K > 0 && K <= kpad && ncols > 0 && ncols % 4 == 0, "ft3d_conv_reduce: bad arguments");
-  FT3D_REQUIRE(((uintptr_t)partial & 15) == 0 && ((uintptr_t)out & 15) == 0, "ft3d_conv_reduce: alignment");
-  conv_reduce_kernel<<<grid_for(n_rows * (ncols >> 2), 256), 256, 0, (cudaStream_t)stream>>>(partial, ppos, n_rows, K,
-                                                                                            kpad, ncols, out);
-  return check_launch("ft3d_conv_reduce");
+  return launch_reduce(partial, ppos, n_rows, kpad, ncols, out, false, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
+                       (cudaStream_t)stream, "ft3d_conv_reduce");
+}
+
+int ft3d_conv_reduce_bn(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
+                        float* out, float eps, float momentum, float* stat, float* running_mean, float* running_var,
+                        void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
+  FT3D_REQUIRE(n_rows > 0, "ft3d_conv_reduce_bn: BatchNorm statistics need at least one row");
+  return launch_reduce(partial, ppos, n_rows, kpad, ncols, out, true, eps, momentum, stat, running_mean, running_var,
+                       workspace, workspace_bytes, (cudaStream_t)stream, "ft3d_conv_reduce_bn");
 }
 
 int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32_t* pairs,

@@ -106,6 +106,7 @@ kmap_emit_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int K, int kpad
     if (lane == 0) s_cnt[warp][k] = __popc(b);
   }
   __syncthreads();
+  int filled = 0;                         // ppos rows are stored compacted: valid positions first, ascending offset
   #pragma unroll
   for (int k = 0; k < 32; ++k) {
     if (k < K && vals[k] >= 0) {
@@ -113,11 +114,11 @@ kmap_emit_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int K, int kpad
       for (int w = 0; w < warp; ++w) pos += s_cnt[w][k];
       pos += __popc(ballots[k] & ((1u << lane) - 1u));
       pairs[pos] = make_int2(vals[k], (int)row);
-      if (ppos) ppos[row * kpad + k] = pos;
-    } else if (ppos && row < n_out && k < kpad) {
-      ppos[row * kpad + k] = -1;
+      if (ppos) ppos[row * kpad + filled++] = pos;
     }
   }
+  if (ppos && row < n_out)
+    for (int j = filled; j < kpad; ++j) ppos[row * kpad + j] = -1;
 }
 
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {

@@ -65,3 +65,18 @@ def voxelize_batch(db: DeviceBatch, scale: float = 20.0, full_scale: int = 4096)
     coords = vc[inds.long()]
     lidar = SparseTensor(coords=coords, feats=db.feats[sel])
     return lidar, db.img_idx[sel].contiguous(), coords[:, 3].contiguous(), db.labels[sel], inv, kept
+
+
+def prepare_batch(batch, device="cuda"):
+    """Everything of a training step that depends only on the batch's points: upload (if ``batch`` is a HostBatch),
+    device-side voxelization + dedup (a1-a3), and the GeometryPlan of the forward pass (plan.py).  Meant to run one
+    step ahead on ``plan.Prefetcher``'s side stream.  Returns the plan; ``plan.extras`` carries
+    ``lidar`` (SparseTensor with ``.plan`` attached), ``rc``, ``bidx``, ``labels``, ``inverse``, ``kept``."""
+    from .plan import build_plan
+    db = to_device(batch, device) if isinstance(batch, HostBatch) else batch
+    lidar, rc, bidx, labels, inv, kept = voxelize_batch(db)
+    plan = build_plan(lidar.C)
+    lidar.plan = plan
+    plan.extras.update(lidar=lidar, rc=rc, bidx=bidx, labels=labels, inverse=inv, kept=kept, batch=db.points,
+                       batch_feats=db.feats, batch_sid=db.scan_id, batch_img=db.img_idx, batch_labels=db.labels)
+    return plan

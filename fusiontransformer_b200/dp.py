@@ -48,6 +48,18 @@ class GradSync:
         if self.world > 1:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._hook)
+        for p in self.params:
+            p._ft3d_sink = self      # fused backward kernels may accumulate straight into the arena (fused.py)
+
+    def owns(self, p) -> bool:
+        """True while ``p.grad`` is still this arena's view (someone may have replaced it, e.g. set_to_none)."""
+        g = p.grad
+        return g is not None and g.untyped_storage().data_ptr() == self.flat.untyped_storage().data_ptr()
+
+    def note(self, p):
+        """A kernel has added p's gradient into the arena (no autograd accumulation => no hook fires)."""
+        if self.world > 1:
+            self._hook(p)
 
     # -- broadcast initial parameters/buffers from rank 0 (what DDP's constructor does)
     def broadcast_parameters(self, module: torch.nn.Module):

@@ -15,7 +15,7 @@ from .sparse_tensor import SparseTensor
 from .utils.kernel_region import KernelRegion
 
 __all__ = ["sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights", "conv3d",
-           "spdownsample", "KernelMap", "lift"]
+           "spdownsample", "KernelMap", "lift", "conv_geometry"]
 
 
 # ------------------------------------------------------------------------ hashing (models/utils.py:19,46-52,74-80)
@@ -99,6 +99,7 @@ class KernelMap:
         self._pposT = None
         self._host_offsets = None
         self._event = None
+        self._num_pairs = None
         self.aux = {}               # per-map caches owned by the conv kernels (tile schedules, ...)
 
     @property
@@ -142,11 +143,15 @@ class KernelMap:
 
     def host_offsets(self):
         self._build_pairs()
-        self._event.synchronize()
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
         return self._host_offsets
 
     def num_pairs(self) -> int:
-        return int(self.host_offsets()[self.K])
+        if self._num_pairs is None:
+            self._num_pairs = int(self.host_offsets()[self.K])
+        return self._num_pairs
 
     def __getitem__(self, i):
         if i == 0:
@@ -259,45 +264,73 @@ class _DenseConv(torch.autograd.Function):
         return gin, gw
 
 
-def conv3d(inputs: SparseTensor, kernel: torch.Tensor, kernel_size: int, bias=None, stride: int = 1,
-           dilation: int = 1, transpose: bool = False) -> SparseTensor:
-    """torchsparse.nn.functional.conv3d v1.1.0 (SURVEY App. A.6); all 49 spnn.Conv3d of models/spvcnn.py."""
-    F, C, s = inputs.F, inputs.C, inputs.s
+def conv_geometry(inputs: SparseTensor, kernel_size: int, stride: int = 1, dilation: int = 1, transpose: bool = False):
+    """Coordinate / kernel-map side of torchsparse conv3d v1.1.0: looks up or builds the map and
+    returns ``(kmap or None for kernel_size 1, make_out)`` where ``make_out(feats)`` wraps the result features in a
+    SparseTensor with the output coordinates, stride and the propagated map caches."""
+    C, s = inputs.C, inputs.s
     if dilation != 1:
         raise NotImplementedError("dilation != 1 is never used by the reference (spvcnn.py) and is not implemented")
     if kernel_size == 1 and stride == 1:
-        from . import conv_engine
-        if conv_engine.pairs_ok(kernel.shape[0], kernel.shape[1]):
-            out = inputs._like(_DenseConv.apply(F, kernel))
-        else:
-            out = inputs._like(F.matmul(kernel))
-        out.check()
-    elif not transpose:
+        def make_out(feats):
+            out = inputs._like(feats)
+            out.check()
+            return out
+        return None, make_out
+    if not transpose:
         key = "k%s_os%d_s%d_d%d" % (kernel_size, s, stride, dilation)
         if stride > 1:
-            new_c = spdownsample(C, stride * s)
-            table = _table_for(inputs, s, C)
-            kmap = build_kernel_map(C, new_c, kernel_size, s, table)
-            out = SparseTensor(_SparseConv.apply(F, kernel, kmap, False), new_c, s * stride)
-            out.coord_maps = dict(inputs.coord_maps)
-            out.kernel_maps = dict(inputs.kernel_maps)
-            out.tables = inputs.tables          # tables are keyed by stride and never invalidated within a pass
-            out.check()
-            out.kernel_maps[key] = kmap
-        else:
             kmap = inputs.kernel_maps.get(key)
-            if kmap is None:
+            new_c = inputs.coord_maps.get(s * stride) if kmap is not None else None
+            if kmap is None or new_c is None:
+                new_c = spdownsample(C, stride * s)
                 table = _table_for(inputs, s, C)
-                kmap = build_kernel_map(C, C, kernel_size, s, table)
-                inputs.kernel_maps[key] = kmap
-            out = inputs._like(_SparseConv.apply(F, kernel, kmap, False))
+                kmap = build_kernel_map(C, new_c, kernel_size, s, table)
+
+            def make_out(feats):
+                out = SparseTensor(feats, new_c, s * stride)
+                out.coord_maps = dict(inputs.coord_maps)
+                out.kernel_maps = dict(inputs.kernel_maps)
+                out.tables = inputs.tables          # tables are keyed by stride and never invalidated within a pass
+                out.check()
+                out.kernel_maps[key] = kmap
+                return out
+            return kmap, make_out
+        kmap = inputs.kernel_maps.get(key)
+        if kmap is None:
+            table = _table_for(inputs, s, C)
+            kmap = build_kernel_map(C, C, kernel_size, s, table)
+            inputs.kernel_maps[key] = kmap
+
+        def make_out(feats):
+            out = inputs._like(feats)
             out.check()
-    else:
-        orig = int(s / stride)
-        kmap = inputs.kernel_maps["k%s_os%d_s%d_d%d" % (kernel_size, orig, stride, dilation)]
-        out = SparseTensor(_SparseConv.apply(F, kernel, kmap, True), inputs.coord_maps[orig], orig)
+            return out
+        return kmap, make_out
+    orig = int(s / stride)
+    kmap = inputs.kernel_maps["k%s_os%d_s%d_d%d" % (kernel_size, orig, stride, dilation)]
+
+    def make_out(feats):
+        out = SparseTensor(feats, inputs.coord_maps[orig], orig)
         out.coord_maps, out.kernel_maps, out.tables = inputs.coord_maps, inputs.kernel_maps, inputs.tables
         out.check()
+        return out
+    return kmap, make_out
+
+
+def conv3d(inputs: SparseTensor, kernel: torch.Tensor, kernel_size: int, bias=None, stride: int = 1,
+           dilation: int = 1, transpose: bool = False) -> SparseTensor:
+    """torchsparse.nn.functional.conv3d v1.1.0 (SURVEY App. A.6); all 49 spnn.Conv3d of models/spvcnn.py."""
+    kmap, make_out = conv_geometry(inputs, kernel_size, stride, dilation, transpose)
+    F = inputs.F
+    if kmap is None:
+        from . import conv_engine
+        if conv_engine.pairs_ok(kernel.shape[0], kernel.shape[1]):
+            out = make_out(_DenseConv.apply(F, kernel))
+        else:
+            out = make_out(F.matmul(kernel))
+    else:
+        out = make_out(_SparseConv.apply(F, kernel, kmap, transpose))
     if bias is not None:
         out.F = out.F + bias
     return out

@@ -1,0 +1,239 @@
+"""Fused execution of the reference's ``Conv3d -> BatchNorm -> ReLU (-> + shortcut -> ReLU)`` module chains.
+
+The reference model code (FusionTransformer/models/spvcnn.py:22-78) strings torchsparse modules together with
+``nn.Sequential``; every link is a separate pass over the activation.  ``fuse(model)`` leaves the modules, their
+parameters and state_dict untouched but re-routes the forward of
+
+  * every ``nn.Sequential`` containing ``Conv3d, BatchNorm[, ReLU]`` runs (BasicConvolutionBlock :22-35,
+    BasicDeconvolutionBlock :38-50, the stem :87-93, ResidualBlock.net / .downsample :57-75), and
+  * every ResidualBlock-shaped module (``net``, ``downsample``, ``relu``; forward :77-79)
+
+through ``conv_bn_act``: one autograd node per convolution whose forward is
+    pair-major tcgen05 GEMM  ->  sorted scatter + BatchNorm statistics  ->  normalise/affine/(+shortcut)/ReLU
+and which hands the next convolution its bf16 operand (``SparseTensor.F16``) instead of re-reading fp32.
+Backward is  BN-backward reduce -> BN-backward apply (emits the bf16 dgrad/wgrad operand) -> dgrad -> wgrad.
+Numerics are those of the unfused path (same kernels, same bf16 rounding points), checked by
+tests/test_gpu_fused.py against the oracle's module-by-module execution.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+from torch import nn
+
+from . import conv_engine, ops
+from . import nn as spnn
+from .functional import conv_geometry
+from .sparse_tensor import SparseTensor
+
+__all__ = ["conv_bn_act", "fuse", "unfuse"]
+
+
+def _role(transpose: bool, grad: bool) -> str:
+    if grad:
+        return "dgrad_transposed" if transpose else "dgrad"
+    return "transposed" if transpose else "forward"
+
+
+class _ConvBNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, kernel, gamma, beta, res, x16, kmap, transpose, relu, bn):
+        ctx.set_materialize_grads(False)         # no zero-filled gradient for the (non-differentiable) bf16 output
+        training = bn.training or bn.running_mean is None
+        rm, rv = (bn.running_mean, bn.running_var) if (bn.training and bn.track_running_stats) else (None, None)
+        cin, cout = kernel.shape[-2], kernel.shape[-1]
+        tc = conv_engine.pairs_ok(cin, cout)
+        stat = None
+        if tc:
+            if x16 is None:
+                x16 = ops.to_bf16(feats)
+            if kmap is None:                                   # kernel_size 1: dense GEMM, rows are already final
+                y = conv_engine.dense_conv(x16, kernel, w_transposed=False)
+            else:
+                partial, ppos, ncols = conv_engine.pairs_partial(x16, kmap, kernel, _role(transpose, False))
+                if training:
+                    y, stat = ops.conv_reduce_bn(partial, ppos, ncols, bn.eps, bn.momentum, rm, rv)
+                else:
+                    y = ops.conv_reduce(partial, ppos, ncols)
+            saved_in = x16
+        else:
+            if kmap is None:
+                y = feats.matmul(kernel)
+            else:
+                table = kmap.nbrT if transpose else kmap.nbr
+                y = conv_engine.gather_conv(feats, table, kmap, kernel, kflip=False, w_transposed=False)
+            saved_in = feats
+        if stat is None:
+            if training:
+                stat = ops.bn_stats(y, bn.eps, bn.momentum, rm, rv)
+            else:
+                stat = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)]).contiguous()
+        z, z16 = ops.bn_apply(y, stat, gamma, beta, res, relu, want_f32=True, want_bf16=tc)
+        ctx.kmap, ctx.transpose, ctx.relu, ctx.tc, ctx.training = kmap, transpose, relu, tc, training
+        ctx.has_res = res is not None
+        mask = (z16 if tc else z) if relu else None
+        ctx.save_for_backward(saved_in, kernel, gamma, y, stat, mask)
+        ctx.beta = beta
+        if z16 is None:
+            z16 = z.new_empty(0)
+        ctx.mark_non_differentiable(z16)
+        return z, z16
+
+    @staticmethod
+    def backward(ctx, gz, _unused):
+        if gz is None:
+            return (None,) * 10
+        saved_in, kernel, gamma, y, stat, mask = ctx.saved_tensors
+        beta = ctx.beta
+        kmap, transpose, tc = ctx.kmap, ctx.transpose, ctx.tc
+        gz = gz.contiguous()
+        m16, m32 = (mask, None) if (mask is not None and mask.dtype == torch.bfloat16) else (None, mask)
+        # Gradient arena (dp.GradSync): parameter gradients are accumulated by the kernels directly into the flat
+        # buffer `.grad` views -- no zero-filled temporaries, no autograd accumulation launches.
+        sink = getattr(kernel, "_ft3d_sink", None)
+        if sink is not None and not (sink.owns(kernel) and sink.owns(gamma) and sink.owns(beta)):
+            sink = None
+        if sink is not None:
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat, gamma.grad, beta.grad)
+        else:
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat)
+        need_in, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        want_res = ctx.has_res and ctx.needs_input_grad[4] and mask is not None
+        gy, gy16, gres = ops.bn_bwd_apply(gz, y, m16, m32, stat, gamma, red if ctx.training else None,
+                                          want_f32=not tc, want_bf16=tc, want_res=want_res)
+        if ctx.has_res and ctx.needs_input_grad[4] and mask is None:
+            gres = gz
+        gin = gw = None
+        cin, cout = kernel.shape[-2], kernel.shape[-1]
+        if tc:
+            if kmap is None:
+                if need_in:
+                    gin = conv_engine.dense_conv(gy16, kernel, w_transposed=True)
+                if need_w:
+                    gw = conv_engine.dense_wgrad(saved_in, gy16, cin, cout, into=kernel.grad if sink else None)
+            else:
+                if need_in:
+                    gin = conv_engine.pairs_conv(gy16, kmap, kernel, _role(transpose, True))
+                if need_w:
+                    gw = conv_engine.pairs_wgrad(saved_in, gy16, kmap, cin, cout, transpose,
+                                                 into=kernel.grad if sink else None)
+            if sink is not None and need_w:
+                gw = None
+                sink.note(kernel)
+        else:
+            if kmap is None:
+                if need_in:
+                    gin = gy.matmul(kernel.t())
+                if need_w:
+                    gw = saved_in.t().matmul(gy)
+            else:
+                if need_in:
+                    if transpose:
+                        table, kflip = kmap.nbr, False
+                    elif kmap.symmetric:
+                        table, kflip = kmap.nbr, True
+                    else:
+                        table, kflip = kmap.nbrT, False
+                    gin = conv_engine.gather_conv(gy, table, kmap, kernel, kflip=kflip, w_transposed=True)
+                if need_w:
+                    gw = conv_engine.wgrad(saved_in, gy, kmap, cin, cout, transpose)
+        if sink is not None:
+            sink.note(gamma)
+            sink.note(beta)
+        return gin, gw, dgamma, dbeta, gres, None, None, None, None, None
+
+
+def _fusable(conv, bn) -> bool:
+    return (isinstance(conv, spnn.Conv3d) and isinstance(bn, nn.BatchNorm1d) and conv.bias is None and bn.affine
+            and bn.momentum is not None and conv.out_channels % 4 == 0 and conv.d == 1)
+
+
+def conv_bn_act(x: SparseTensor, conv, bn, relu: bool, res: torch.Tensor | None = None) -> SparseTensor:
+    """``relu?(bn(conv(x)) [+ res])`` as one autograd node; ``res`` is an fp32 [N_out, Cout] tensor."""
+    kmap, make_out = conv_geometry(x, conv.ks, conv.s, conv.d, conv.t)
+    feats = x.F
+    if not feats.is_contiguous():
+        feats = feats.contiguous()
+    x16 = x.F16
+    if x16 is not None and (x16.shape != feats.shape or x16.dtype != torch.bfloat16):
+        x16 = None
+    z, z16 = _ConvBNAct.apply(feats, conv.kernel, bn.weight, bn.bias, res, x16, kmap, conv.t, relu, bn)
+    if bn.training and bn.track_running_stats:
+        bn._ft3d_pending_batches = getattr(bn, "_ft3d_pending_batches", 0) + 1
+    out = make_out(z)
+    if z16.numel():
+        out.F16 = z16
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ module re-routing
+def _flush_batches(module, *_):
+    """num_batches_tracked is kept on the host between state_dict() calls (one fewer launch per BatchNorm per step)."""
+    n = getattr(module, "_ft3d_pending_batches", 0)
+    if n and module.num_batches_tracked is not None:
+        module.num_batches_tracked += n
+    module._ft3d_pending_batches = 0
+
+
+def _sequential_forward(self, x):
+    mods = list(self._modules.values())
+    i, n = 0, len(mods)
+    while i < n:
+        m = mods[i]
+        if (isinstance(x, SparseTensor) and i + 1 < n and _fusable(m, mods[i + 1]) and x.F.is_cuda):
+            relu = i + 2 < n and type(mods[i + 2]) is spnn.ReLU
+            x = conv_bn_act(x, m, mods[i + 1], relu)
+            i += 3 if relu else 2
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
+def _is_residual_block(m) -> bool:
+    net, ds, relu = getattr(m, "net", None), getattr(m, "downsample", None), getattr(m, "relu", None)
+    if not (isinstance(net, nn.Sequential) and isinstance(ds, nn.Sequential) and type(relu) is spnn.ReLU):
+        return False
+    nm, dm = list(net), list(ds)
+    if len(nm) != 5 or not (_fusable(nm[0], nm[1]) and type(nm[2]) is spnn.ReLU and _fusable(nm[3], nm[4])):
+        return False
+    return len(dm) == 0 or (len(dm) == 2 and _fusable(dm[0], dm[1]))
+
+
+def _residual_forward(self, x):
+    if not (isinstance(x, SparseTensor) and x.F.is_cuda):
+        return self.relu(self.net(x) + self.downsample(x))
+    nm, dm = list(self.net), list(self.downsample)
+    h = conv_bn_act(x, nm[0], nm[1], True)
+    shortcut = x.F if not dm else conv_bn_act(x, dm[0], dm[1], False).F
+    return conv_bn_act(h, nm[3], nm[4], True, res=shortcut.contiguous())
+
+
+def fuse(model: nn.Module) -> nn.Module:
+    """Re-route the conv/BN/ReLU chains of ``model`` (in place) through the fused kernels; returns ``model``."""
+    for m in model.modules():
+        if getattr(m, "_ft3d_fused", False):
+            continue
+        if _is_residual_block(m):
+            m.forward = types.MethodType(_residual_forward, m)
+            m._ft3d_fused = True
+        elif isinstance(m, nn.Sequential):
+            mods = list(m)
+            if any(_fusable(a, b) for a, b in zip(mods, mods[1:])):
+                m.forward = types.MethodType(_sequential_forward, m)
+                m._ft3d_fused = True
+        if isinstance(m, nn.BatchNorm1d) and not getattr(m, "_ft3d_hooked", False):
+            m.register_state_dict_pre_hook(_flush_batches)
+            m._ft3d_hooked = True
+    return model
+
+
+def unfuse(model: nn.Module) -> nn.Module:
+    for m in model.modules():
+        if getattr(m, "_ft3d_fused", False):
+            del m.forward
+            m._ft3d_fused = False
+        if isinstance(m, nn.BatchNorm1d):
+            _flush_batches(m)
+    return model

@@ -13,8 +13,13 @@ from ._lib import Ft3dError, lib
 KPAD = {27: 32, 8: 8}
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_dev = torch.cuda.current_device
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream (the C accessor: ~0.2 us, vs ~3 us for torch.cuda.current_stream())."""
+    return _raw_stream(_cur_dev())
 
 
 def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
@@ -395,17 +400,93 @@ def conv_pairs_tc(x16, pairs, offsets, k, gather_col, max_pairs, w, w_transposed
     return partial
 
 
-def conv_reduce(partial, ppos, k, ncols):
+def conv_reduce(partial, ppos, ncols):
     n_rows, kpad = ppos.shape
     out = torch.empty((n_rows, ncols), dtype=torch.float32, device=partial.device)
-    lib().conv_reduce(partial.data_ptr(), ppos.data_ptr(), n_rows, k, kpad, ncols, out.data_ptr(), _stream())
+    lib().conv_reduce(partial.data_ptr(), ppos.data_ptr(), n_rows, kpad, ncols, out.data_ptr(), _stream())
     return out
 
 
-def conv_wgrad_pairs_tc(a16, b16, pairs, offsets, k, ca, cin, cout, max_pairs):
+# ----------------------------------------------------------------------------- fused BatchNorm / ReLU / residual
+_BN_SCRATCH = {}
+
+
+def bn_scratch(device):
+    """Partial-row workspace of the deterministic column reductions; one per (device, stream): kernels on a stream
+    are ordered, so every layer can share it."""
+    key = (device.index, _stream())
+    hit = _BN_SCRATCH.get(key)
+    if hit is None:
+        hit = torch.empty(int(lib().bn_workspace(1024)), dtype=torch.uint8, device=device)
+        _BN_SCRATCH[key] = hit
+    return hit
+
+
+def conv_reduce_bn(partial, ppos, ncols, eps, momentum, running_mean, running_var):
+    """sorted scatter + BatchNorm training statistics: returns (y [n,ncols] f32, stat [2,ncols] f32)."""
+    n_rows, kpad = ppos.shape
+    dev = partial.device
+    out = torch.empty((n_rows, ncols), dtype=torch.float32, device=dev)
+    stat = torch.empty((2, ncols), dtype=torch.float32, device=dev)
+    ws = bn_scratch(dev)
+    lib().conv_reduce_bn(partial.data_ptr(), ppos.data_ptr(), n_rows, kpad, ncols, out.data_ptr(), float(eps),
+                         float(momentum), stat.data_ptr(), _p(running_mean), _p(running_var), ws.data_ptr(), ws.numel(),
+                         _stream())
+    return out, stat
+
+
+def bn_stats(y, eps, momentum, running_mean, running_var):
+    n, c = y.shape
+    stat = torch.empty((2, c), dtype=torch.float32, device=y.device)
+    ws = bn_scratch(y.device)
+    lib().bn_stats(y.data_ptr(), n, c, float(eps), float(momentum), stat.data_ptr(), _p(running_mean), _p(running_var),
+                   ws.data_ptr(), ws.numel(), _stream())
+    return stat
+
+
+def bn_apply(y, stat, gamma, beta, res, relu: bool, want_f32: bool = True, want_bf16: bool = True):
+    n, c = y.shape
+    z = torch.empty((n, c), dtype=torch.float32, device=y.device) if want_f32 else None
+    z16 = torch.empty((n, c), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    lib().bn_apply(y.data_ptr(), n, c, stat.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(res), int(relu), _p(z),
+                   _p(z16), _stream())
+    return z, z16
+
+
+def bn_bwd_reduce(gz, y, z16, z, stat, dgamma_into=None, dbeta_into=None):
+    """-> (red [2,C], dgamma [C], dbeta [C]); with ``*_into`` the sums are ADDED to those tensors (gradient arena)
+    and (red, None, None) is returned."""
+    n, c = y.shape
+    dev = y.device
+    red = torch.empty((2, c), dtype=torch.float32, device=dev)
+    ws = bn_scratch(dev)
+    if dgamma_into is not None:
+        lib().bn_bwd_reduce(gz.data_ptr(), y.data_ptr(), _p(z16), _p(z), n, c, stat.data_ptr(), red.data_ptr(),
+                            dgamma_into.data_ptr(), dbeta_into.data_ptr(), 1, ws.data_ptr(), ws.numel(), _stream())
+        return red, None, None
+    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    lib().bn_bwd_reduce(gz.data_ptr(), y.data_ptr(), _p(z16), _p(z), n, c, stat.data_ptr(), red.data_ptr(),
+                        dgb[0].data_ptr(), dgb[1].data_ptr(), 0, ws.data_ptr(), ws.numel(), _stream())
+    return red, dgb[0], dgb[1]
+
+
+def bn_bwd_apply(gz, y, z16, z, stat, gamma, red, want_f32: bool, want_bf16: bool, want_res: bool):
+    n, c = gz.shape
+    dev = gz.device
+    gy = torch.empty((n, c), dtype=torch.float32, device=dev) if want_f32 else None
+    gy16 = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    gres = torch.empty((n, c), dtype=torch.float32, device=dev) if want_res else None
+    lib().bn_bwd_apply(gz.data_ptr(), _p(y), _p(z16), _p(z), n, c, stat.data_ptr(), gamma.data_ptr(), _p(red), _p(gy),
+                       _p(gy16), _p(gres), _stream())
+    return gy, gy16, gres
+
+
+def conv_wgrad_pairs_tc(a16, b16, pairs, offsets, k, ca, cin, cout, max_pairs, into=None):
+    """``into``: an fp32 tensor of k*cin*cout elements that the gradient is ACCUMULATED into (the kernel adds with
+    atomics anyway); otherwise a fresh zero-filled tensor is returned."""
     a16 = _chk(a16, torch.bfloat16, "a16")
     b16 = _chk(b16, torch.bfloat16, "b16")
-    gw = torch.zeros((k, cin, cout), dtype=torch.float32, device=a16.device)
+    gw = into if into is not None else torch.zeros((k, cin, cout), dtype=torch.float32, device=a16.device)
     lib().conv_wgrad_pairs_tc(a16.data_ptr(), b16.data_ptr(), _p(pairs), _p(offsets), k, int(ca), cin, cout,
                               int(max_pairs), gw.data_ptr(), _stream())
     return gw

@@ -14,12 +14,32 @@ __all__ = ["SparseTensor"]
 
 class SparseTensor:
     def __init__(self, feats, coords, stride=1):
+        self._F16 = None
         self.F = feats
         self.C = coords
         self.s = stride
         self.coord_maps = {}
         self.kernel_maps = {}
         self.tables = {}
+
+    # ``F16``: bf16 copy of ``F`` written by the fused conv+BN+ReLU epilogue (csrc/bn.cu) -- the operand the next
+    # tensor-core convolution gathers.  Assigning ``F`` drops it, so it can never go stale.
+    @property
+    def F(self):
+        return self._F
+
+    @F.setter
+    def F(self, value):
+        self._F = value
+        self._F16 = None
+
+    @property
+    def F16(self):
+        return self._F16
+
+    @F16.setter
+    def F16(self, value):
+        self._F16 = value
 
     def check(self):
         if self.s not in self.coord_maps:

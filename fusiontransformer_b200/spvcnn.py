@@ -8,6 +8,8 @@ the reference's own model files run unmodified after ``install_as_torchsparse()`
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -91,6 +93,9 @@ class SPVCNN(nn.Module):
                                                _point_mlp(cs[6], cs[8])])
         self.weight_initialization()
         self.dropout = nn.Dropout(0.3, True)
+        if os.environ.get("FT3D_FUSE", "1") != "0":
+            from .fused import fuse
+            fuse(self)                      # conv+BN+ReLU(+shortcut) chains run as fused kernels; modules unchanged
 
     def weight_initialization(self):
         for m in self.modules():
@@ -98,11 +103,12 @@ class SPVCNN(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
-    def backbone(self, x: SparseTensor, early_feats=None, middle_feats=None, taps=None):
+    def backbone(self, x: SparseTensor, early_feats=None, middle_feats=None, taps=None, plan=None):
         """spvcnn.py:191-233.  ``early_feats`` [N,32] is added at z0 (early_fusion.py:39), ``middle_feats``
         [N,256] at z1 (middle_fusion.py:48); both already passed through their fusion MLP."""
-        z = PointTensor(x.F, x.C.float())
-        x0 = initial_voxelize(z, self.pres, self.vres)
+        plan = plan if plan is not None else getattr(x, "plan", None)     # plan.py: geometry built one step ahead
+        z = PointTensor(x.F, x.C.float() if plan is None else plan.point_coords)
+        x0 = initial_voxelize(z, self.pres, self.vres, plan=plan)
         x0 = self.stem(x0)
         z0 = voxel_to_point(x0, z, nearest=False)
         if early_feats is not None:
@@ -157,13 +163,13 @@ class Net3DSeg(SPVCNN):
         if dual_head:
             self.linear2 = nn.Linear(self.cs[-1], num_classes)
 
-    def forward(self, x, img_feats=None, taps=None):
+    def forward(self, x, img_feats=None, taps=None, plan=None):
         early = middle = None
         if self.fusion == "middle":
             middle = self.middle_fusion_transform(img_feats)
         elif self.fusion == "early":
             early = self.early_fusion_transform(img_feats)
-        feats = self.backbone(x, early_feats=early, middle_feats=middle, taps=taps)
+        feats = self.backbone(x, early_feats=early, middle_feats=middle, taps=taps, plan=plan)
         preds = {"lidar_feats": feats, "lidar_seg_logit": self.linear(feats)}
         if self.dual_head:
             preds["lidar_seg_logit2"] = self.linear2(feats)

@@ -19,7 +19,9 @@ from .sparse_tensor import SparseTensor
 __all__ = ["initial_voxelize", "point_to_voxel", "voxel_to_point"]
 
 
-def initial_voxelize(z: PointTensor, init_res, after_res) -> SparseTensor:
+def initial_voxelize(z: PointTensor, init_res, after_res, plan=None) -> SparseTensor:
+    if plan is not None:
+        return _initial_voxelize_planned(z, init_res, after_res, plan)
     new_float_coord = torch.cat([(z.C[:, :3] * init_res) / after_res, z.C[:, -1].view(-1, 1)], 1)
     coords = torch.floor(new_float_coord).int()
     pc_hash = ops.hash_coords(coords)
@@ -34,6 +36,27 @@ def initial_voxelize(z: PointTensor, init_res, after_res) -> SparseTensor:
     z.additional_features["idx_query"][1] = idx_query
     z.additional_features["counts"][1] = counts
     z.C = new_float_coord
+    return new_tensor
+
+
+def _initial_voxelize_planned(z: PointTensor, init_res, after_res, plan) -> SparseTensor:
+    """Same result as above with every integer structure taken from a GeometryPlan (plan.py) built ahead of time."""
+    if init_res != after_res:
+        raise ValueError("a GeometryPlan is built for pres == vres (the reference's configuration)")
+    new_tensor = SparseTensor(_Voxelize.apply(z.F.float().contiguous(), plan.idx_query, plan.counts),
+                              plan.coord_maps[1], 1)
+    new_tensor.coord_maps = dict(plan.coord_maps)
+    new_tensor.kernel_maps = dict(plan.kernel_maps)
+    new_tensor.tables = dict(plan.tables)
+    z.additional_features["idx_query"][1] = plan.idx_query
+    z.additional_features["counts"][1] = plan.counts
+    for s, (idx, cnt) in plan.p2v.items():
+        z.additional_features["idx_query"][s] = idx
+        z.additional_features["counts"][s] = cnt
+    for s, (idx, w) in plan.v2p.items():
+        z.idx_query[s] = idx
+        z.weights[s] = w
+    z.C = plan.point_coords
     return new_tensor
 
 

@@ -90,12 +90,14 @@ int ft3d_kmap_build(const int32_t* coords_q, int64_t n_out, const int32_t* offse
  * (in,out), offset-major then out-ascending; offsets_out int32 [K+1] exclusive prefix of the
  * per-offset counts (offsets_out[K] = L).  pairs_out must hold K*n_out rows. */
 size_t ft3d_kmap_pairs_workspace(int64_t n_out, int32_t kpad);
-/* ppos_out (nullable) int32 [n_out,kpad]: position of pair (row j, offset k) in pairs_out, -1 if absent. */
+/* ppos_out (nullable) int32 [n_out,kpad]: the positions in pairs_out of row j's pairs, compacted to the front of the
+ * row in ascending offset order and terminated by -1 (the row is the CSR segment of output j, pitch kpad). */
 int ft3d_kmap_pairs(const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad,
                     int32_t* pairs_out, int32_t* offsets_out, int32_t* ppos_out, void* workspace,
                     size_t workspace_bytes, ft3d_stream_t stream);
-/* ppos_out int32 [n_rows,kpad]: ppos_out[pairs[p][col]][k(p)] = p, -1 elsewhere -- the pair-position table seen
- * from the other side of the map (col 0: input rows, for dgrad and transposed conv; col 1 reproduces the above). */
+/* ppos_out int32 [n_rows,kpad]: the same compacted pair-position rows seen from the other side of the map: row
+ * r lists, in ascending offset order, the positions p with pairs[p][col] == r (col 0: input rows, for dgrad and
+ * transposed conv; col 1 reproduces the table of ft3d_kmap_pairs). */
 int ft3d_kmap_pair_positions(const int32_t* pairs, const int32_t* pair_offsets, int32_t K, int32_t kpad,
                              int32_t col, int64_t n_rows, int64_t max_pairs, int32_t* ppos_out,
                              ft3d_stream_t stream);
@@ -177,19 +179,51 @@ int ft3d_conv_wgrad_tc(const float* a, const float* b, const int32_t* pairs,
  *                         pair order; tcgen05.mma, fp32 accumulate in TMEM).  pairs == NULL (with K == 1) is the
  *                         identity gather over max_pairs rows: a dense GEMM (k = 1 convolutions, torchsparse
  *                         conv3d kernel_size 1 == F.matmul) whose partial_out IS the result.
- *   ft3d_conv_reduce    : out[row,:] = sum_k partial[ppos[row,k],:] in ascending k (deterministic, no atomics).
+ *   ft3d_conv_reduce    : out[row,:] = sum_j partial[ppos[row,j],:] over the row's compacted positions, i.e. in
+ *                         ascending offset order (deterministic, no atomics, every output row written once).
+ *   ft3d_conv_reduce_bn : the same pass also folds the per-channel sum / sum of squares of the rows it writes and
+ *                         leaves this layer's BatchNorm training statistics in stat (see ft3d_bn_stats).
  *   forward: gather_col 0, ppos of ft3d_kmap_pairs;   dgrad / transposed conv: gather_col 1, ppos of
  *   ft3d_kmap_pair_positions(col 0) and the w_transposed weight image. */
 int ft3d_to_bf16(const float* src, int64_t n, void* dst, ft3d_stream_t stream);
 int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t* pair_offsets, int32_t K,
                        int32_t gather_col, int64_t max_pairs, int32_t red, int32_t ncols,
                        const void* wpacked, float* partial_out, ft3d_stream_t stream);
-int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t K, int32_t kpad,
-                     int32_t ncols, float* out, ft3d_stream_t stream);
+int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
+                     float* out, ft3d_stream_t stream);
+int ft3d_conv_reduce_bn(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
+                        float* out, float eps, float momentum, float* stat, float* running_mean,
+                        float* running_var, void* workspace, size_t workspace_bytes, ft3d_stream_t stream);
 /* wgrad on bf16 inputs: gw[k] += a_bf16[pairs[p][ca],:]^T b_bf16[pairs[p][1-ca],:]; pairs == NULL: identity (K == 1). */
 int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32_t* pairs,
                              const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin, int32_t cout,
                              int64_t max_pairs, float* gw, ft3d_stream_t stream);
+
+/* ---- a11  spnn.BatchNorm / spnn.ReLU / residual add fused around the convolution
+ *          (models/spvcnn.py:26-31,42-47,57-78; torchsparse BatchNorm == nn.BatchNorm1d on .F) ---------------- */
+/* Column reductions are deterministic: per-CTA partial rows in `workspace` (ft3d_bn_workspace(C) bytes), folded in
+ * double by a second tiny launch with a fixed-shape tree; no float atomics.  stat f32 [2,C] = (batch mean,
+ * 1/sqrt(biased var + eps)); running_mean/var (nullable pair) are updated with `momentum` and the unbiased variance
+ * exactly as nn.BatchNorm1d does in training mode. */
+size_t ft3d_bn_workspace(int32_t channels);
+int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float momentum, float* stat,
+                  float* running_mean, float* running_var, void* workspace, size_t workspace_bytes,
+                  ft3d_stream_t stream);
+/* z = [relu]((y - mean) * rstd * gamma + beta [+ res]); writes z f32 [n,C] (nullable) and z16 bf16 [n,C]
+ * (nullable) -- the copy the next convolution gathers.  Evaluation mode: pass stat built from the running stats. */
+int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma,
+                  const float* beta, const float* res, int32_t relu, float* z, void* z16, ft3d_stream_t stream);
+/* g' = gz * [z > 0] (mask from z16 if given, else z, else none).  red f32 [2,C] = (sum g'/n, sum g' xhat/n);
+ * dgamma = sum g' xhat; dbeta = sum g' (accumulate != 0: added to the values already there, so the gradients can
+ * be written straight into a flat gradient arena). */
+int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const float* z, int64_t n,
+                       int32_t channels, const float* stat, float* red, float* dgamma, float* dbeta,
+                       int32_t accumulate, void* workspace, size_t workspace_bytes, ft3d_stream_t stream);
+/* gy = gamma rstd (g' - c1 - xhat c2)  (red == NULL: frozen statistics, gy = gamma rstd g'); outputs (each
+ * nullable): gy f32, gy16 bf16 (the dgrad / wgrad operand), gres f32 = g' (gradient of the residual input). */
+int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const float* z, int64_t n,
+                      int32_t channels, const float* stat, const float* gamma, const float* red, float* gy,
+                      void* gy16, float* gres, ft3d_stream_t stream);
 
 #ifdef __cplusplus
 }

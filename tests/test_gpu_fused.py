@@ -1,0 +1,229 @@
+"""Fused conv + BatchNorm + ReLU (+ shortcut) blocks (csrc/bn.cu, fused.py) vs the oracle's module-by-module chain.
+
+The oracle executes spvcnn.py:22-79 literally (Conv3d, nn.BatchNorm1d, ReLU as separate modules); the product runs
+each chain as one autograd node.  f32 mode is held to 1e-4 (fp32 summation order only), tc mode to the per-layer
+5e-3 of the north star with the oracle computing on bf16-rounded conv operands (oracle.ts_ops.OPERAND_DTYPE).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def voxels(small_batch):
+    from oracle import ft_glue as og, ts_ops as ts
+    z = ts.PointTensor(small_batch["feats"], small_batch["coords"].float())
+    return og.initial_voxelize(z, 1, 1)
+
+
+def _mirror(block_o, build):
+    """The product's module with the oracle's parameters."""
+    m = build()
+    m.load_state_dict(block_o.state_dict())
+    return m.cuda()
+
+
+def _check_grads(mo, mg, tol, what):
+    for (name, po), (_, pg) in zip(mo.named_parameters(), mg.named_parameters()):
+        assert pg.grad is not None, (what, name)
+        scale = max(po.grad.norm().item(), 1e-6)
+        err = (pg.grad.double().cpu() - po.grad.double()).norm().item() / scale
+        assert err < tol, (what, name, err)
+
+
+def _check_buffers(mo, mg, tol, what):
+    bo, bg = dict(mo.named_buffers()), dict(mg.state_dict())
+    for name, b in bo.items():
+        if name.endswith("num_batches_tracked"):
+            assert int(bg[name]) == int(b), (what, name)
+        else:
+            assert rel_l2(bg[name], b) < tol, (what, name)
+
+
+CASES = [  # (kind, cin, cout)
+    ("k3", 32, 64), ("k3", 96, 96), ("k3", 4, 32), ("down", 32, 32), ("res_identity", 64, 64), ("res_proj", 64, 128),
+]
+
+
+@pytest.mark.parametrize("mode,tol", [("f32", 1e-4), ("tc", 5e-3)])
+@pytest.mark.parametrize("kind,cin,cout", CASES)
+def test_fused_block_matches_module_chain(monkeypatch, voxels, mode, tol, kind, cin, cout):
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import spvcnn as sp
+    from oracle import ft_glue as og, ts_ops as ts
+    monkeypatch.setenv("FT3D_CONV", mode)
+    monkeypatch.setattr(ts, "OPERAND_DTYPE", "bf16" if mode == "tc" else None)
+    torch.manual_seed(cin * 7 + cout)
+    if kind == "k3":
+        mo = og._Block(cin, cout, 3, 1)
+        mg = _mirror(mo, lambda: sp.BasicConvolutionBlock(cin, cout, ks=3, stride=1))
+    elif kind == "down":
+        mo = og._Block(cin, cout, 2, 2)
+        mg = _mirror(mo, lambda: sp.BasicConvolutionBlock(cin, cout, ks=2, stride=2))
+    else:
+        mo = og.ResidualBlock(cin, cout, 3, 1)
+        mg = _mirror(mo, lambda: sp.ResidualBlock(cin, cout, ks=3, stride=1))
+    for p in list(mo.parameters()):          # non-trivial affine parameters
+        if p.dim() == 1:
+            p.data.uniform_(0.5, 1.5)
+    mg.load_state_dict(mo.state_dict())
+    ft.fuse(mg)
+    assert any(getattr(m, "_ft3d_fused", False) for m in mg.modules())
+    mo.train(), mg.train()
+    C = voxels.C
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(C.shape[0], cin, generator=g)
+    fo = feats.clone().requires_grad_(True)
+    xo = ts.SparseTensor(fo, C, 1)
+    xo.check()
+    yo = mo(xo)
+    gsel = torch.randn(yo.F.shape, generator=g)
+    (yo.F * gsel).sum().backward()
+    fg = feats.cuda().requires_grad_(True)
+    xg = ft.SparseTensor(fg, C.cuda(), 1)
+    xg.check()
+    yg = mg(xg)
+    assert torch.equal(yg.C.cpu(), yo.C.int()) and yg.s == yo.s
+    assert rel_l2(yg.F, yo.F) < tol
+    if mode == "tc" and cin % 16 == 0:
+        assert yg.F16 is not None and torch.equal(yg.F16, yg.F.to(torch.bfloat16))   # the next conv's operand
+    (yg.F * gsel.cuda()).sum().backward()
+    assert rel_l2(fg.grad, fo.grad) < 4 * tol
+    _check_grads(mo, mg, 6 * tol, kind)
+    _check_buffers(mo, mg, max(tol, 1e-5), kind)
+
+
+@pytest.mark.parametrize("mode,tol", [("f32", 1e-4), ("tc", 5e-3)])
+def test_fused_down_up_chain(monkeypatch, voxels, mode, tol):
+    """stride-2 conv block followed by the transposed block that reuses its map (spvcnn.py:22-50)."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import spvcnn as sp
+    from oracle import ft_glue as og, ts_ops as ts
+    monkeypatch.setenv("FT3D_CONV", mode)
+    monkeypatch.setattr(ts, "OPERAND_DTYPE", "bf16" if mode == "tc" else None)
+    torch.manual_seed(11)
+    mo = torch.nn.Sequential(og._Block(32, 64, 2, 2), og._Block(64, 96, 2, 2, transpose=True))
+    mg = torch.nn.Sequential(sp.BasicConvolutionBlock(32, 64, ks=2, stride=2),
+                             sp.BasicDeconvolutionBlock(64, 96, ks=2, stride=2))
+    mg.load_state_dict(mo.state_dict())
+    mg = ft.fuse(mg.cuda())
+    mo.train(), mg.train()
+    C = voxels.C
+    g = torch.Generator().manual_seed(6)
+    feats = torch.randn(C.shape[0], 32, generator=g)
+    fo = feats.clone().requires_grad_(True)
+    xo = ts.SparseTensor(fo, C, 1)
+    xo.check()
+    yo = mo(xo)
+    gsel = torch.randn(yo.F.shape, generator=g)
+    (yo.F * gsel).sum().backward()
+    fg = feats.cuda().requires_grad_(True)
+    xg = ft.SparseTensor(fg, C.cuda(), 1)
+    xg.check()
+    yg = mg(xg)
+    assert yg.s == 1 and torch.equal(yg.C.cpu(), C.int())
+    assert rel_l2(yg.F, yo.F) < 2 * tol
+    (yg.F * gsel.cuda()).sum().backward()
+    assert rel_l2(fg.grad, fo.grad) < 6 * tol
+    _check_grads(mo, mg, 8 * tol, "down_up")
+
+
+def test_fused_eval_mode_uses_running_statistics(monkeypatch, voxels):
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import spvcnn as sp
+    from oracle import ft_glue as og, ts_ops as ts
+    monkeypatch.setenv("FT3D_CONV", "f32")
+    monkeypatch.setattr(ts, "OPERAND_DTYPE", None)
+    torch.manual_seed(3)
+    mo = og.ResidualBlock(32, 64, 3, 1)
+    for name, b in mo.named_buffers():
+        if name.endswith("running_mean"):
+            b.uniform_(-0.5, 0.5)
+        elif name.endswith("running_var"):
+            b.uniform_(0.5, 2.0)
+    mg = sp.ResidualBlock(32, 64, ks=3, stride=1)
+    mg.load_state_dict(mo.state_dict())
+    mg = ft.fuse(mg.cuda())
+    mo.eval(), mg.eval()
+    C = voxels.C
+    feats = torch.randn(C.shape[0], 32, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        yo = mo(ts.SparseTensor(feats, C, 1))
+        yg = mg(ft.SparseTensor(feats.cuda(), C.cuda(), 1))
+    assert rel_l2(yg.F, yo.F) < 1e-5
+
+
+@pytest.mark.parametrize("mode,tol", [("f32", 2e-4), ("tc", 1e-2)])
+def test_fused_model_matches_unfused_model(monkeypatch, small_batch, mode, tol):
+    """Whole 3D branch: fused and unfused execution of the same parameters on the GPU agree (same kernels and
+    rounding points; only the BatchNorm reduction order differs)."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200.spvcnn import Net3DSeg
+    monkeypatch.setenv("FT3D_CONV", mode)
+    torch.manual_seed(1)
+    a = Net3DSeg(fusion="middle").cuda().train()
+    b = Net3DSeg(fusion="middle").cuda().train()
+    b.load_state_dict(a.state_dict())
+    ft.unfuse(b)
+    a.dropout.p = b.dropout.p = 0.0
+    coords, feats = small_batch["coords"].cuda(), small_batch["feats"].cuda()
+    n = coords.shape[0]
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(n, 96, generator=g).cuda()
+    labels = torch.randint(0, 20, (n,), generator=g).cuda()
+    outs = []
+    for net in (a, b):
+        out = net(ft.SparseTensor(feats, coords), img)["lidar_seg_logit"]
+        torch.nn.functional.cross_entropy(out, labels).backward()
+        outs.append(out)
+    assert rel_l2(outs[0], outs[1]) < tol
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]) == 1, k
+        elif "running_" in k:
+            assert rel_l2(sa[k], sb[k]) < max(tol, 1e-4), k
+    if mode == "f32":
+        gmax = max(p.grad.norm().item() for p in b.parameters() if p.grad is not None)
+        for (name, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            err = (pa.grad - pb.grad).norm().item() / max(pb.grad.norm().item(), 1e-4 * gmax)
+            assert err < 5e-2, (name, err)
+
+
+def test_gradient_arena_sink_equals_autograd_accumulation(monkeypatch, voxels):
+    """dp.GradSync arena: fused backward kernels add parameter gradients straight into the flat buffer; the result
+    equals ordinary autograd accumulation into fresh .grad tensors (two blocks deep, so that bf16 rounding flips of
+    the ~50-BatchNorm network do not enter: DESIGN.md "Tolerances")."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import spvcnn as sp
+    from fusiontransformer_b200.dp import GradSync
+    monkeypatch.setenv("FT3D_CONV", "tc")
+    torch.manual_seed(1)
+
+    def build():
+        return torch.nn.Sequential(sp.BasicConvolutionBlock(32, 64, ks=2, stride=2), sp.ResidualBlock(64, 128),
+                                   sp.BasicDeconvolutionBlock(128, 32, ks=2, stride=2))
+    a, b = ft.fuse(build().cuda().train()), ft.fuse(build().cuda().train())
+    b.load_state_dict(a.state_dict())
+    sync = GradSync(a)
+    C = voxels.C.cuda()
+    g = torch.Generator().manual_seed(3)
+    feats = torch.randn(C.shape[0], 32, generator=g).cuda()
+    gsel = torch.randn(C.shape[0], 32, generator=g).cuda()
+    for _ in range(2):                                   # second pass: the arena is re-zeroed, not re-allocated
+        sync.zero_grad()
+        b.zero_grad(set_to_none=True)
+        for net in (a, b):
+            x = ft.SparseTensor(feats, C, 1)
+            x.check()
+            (net(x).F * gsel).sum().backward()
+        sync.finish()
+    for (name, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert sync.owns(pa), name
+        assert (pa.grad - pb.grad).norm().item() <= 1e-3 * pb.grad.norm().item() + 1e-7, name

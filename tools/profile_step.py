@@ -13,6 +13,7 @@ def main():
     ap.add_argument("--workload", default="nuscenes")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--cprofile", action="store_true", help="host-side cProfile of the step instead of the GPU timeline")
     a = ap.parse_args()
     import fusiontransformer_b200 as ft
     from fusiontransformer_b200 import dataflow
@@ -45,6 +46,20 @@ def main():
         step()
     torch.cuda.synchronize()
     import time
+    if a.cprofile:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        t0 = time.perf_counter()
+        pr.enable()
+        for _ in range(a.steps):
+            step()
+        pr.disable()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        print("host ms/step to enqueue (cProfile on): %.2f" % ((t1 - t0) / a.steps * 1e3))
+        pstats.Stats(pr).sort_stats("tottime").print_stats(a.top)
+        return
     t0 = time.perf_counter()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for _ in range(a.steps):
