@@ -156,13 +156,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="nuscenes", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="scans per GPU per step (default: the workload's)")
     ap.add_argument("--fusion", default="middle", choices=["none", "middle", "early"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--prefetch-thread", dest="no_prefetch_thread", action="store_false",
+                    help="build the next batch's geometry from a worker thread (GIL-bound: slower)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch every kernel of the step from Python instead of replaying the captured CUDA graph")
+    ap.add_argument("--reuse-plans", action="store_true", help="diagnostic only: time the compute with cached geometry")
     ap.add_argument("--diag", action="store_true", help="print host-side enqueue time per phase (stderr)")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="build each batch's geometry inside its own step (host reads stall the launch queue)")
@@ -209,12 +214,13 @@ def main():
     net = Net3DSeg(num_classes=20, dual_head=False, fusion=args.fusion).to(dev).train()
     sync = GradSync(net)
     sync.broadcast_parameters(net)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=5e-4, fused=True)
+    use_graph = args.graph and conv_engine.mode() == "tc"
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=5e-4, fused=True, capturable=use_graph)
 
     # The geometry of batch i+1 (upload, voxelization, kernel maps: every host read of a data-dependent size) is
     # built on a high-priority side stream while batch i's convolutions run (fusiontransformer_b200/plan.py).
     from fusiontransformer_b200.plan import Prefetcher
-    pre = Prefetcher(dev) if args.prefetch else None
+    pre = Prefetcher(dev, threaded=not args.no_prefetch_thread) if args.prefetch else None
 
     diag = {} if args.diag else None
 
@@ -223,28 +229,70 @@ def main():
             diag[name] = diag.get(name, 0.0) + (time.perf_counter() - t0)
         return time.perf_counter()
 
-    def train_step(batch, nxt=None):
-        t = time.perf_counter()
-        if pre is None:
-            plan = dataflow.prepare_batch(batch, dev)
-        else:
-            if pre._pending is None:
-                pre.submit(dataflow.prepare_batch, batch, dev)
-            plan = pre.get()
-        t = tick("get_plan", t)
+    def fwd_bwd(plan):
         ex = plan.extras
         img = ft.nn.functional.lift(fmap, ex["rc"], ex["bidx"]) if args.fusion != "none" else None
         out = net(ex["lidar"], None if img is None else img.detach())
         loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], ex["labels"])
-        t = tick("forward", t)
         sync.zero_grad()
         loss.backward()
-        t = tick("backward", t)
-        sync.finish()
-        opt.step()
-        t = tick("optimizer", t)
+        return loss
+
+    # The compute of a step (lift, forward, loss, backward, optimizer) is captured once per capacity set as ONE CUDA
+    # graph and replayed on capacity-padded geometry (fusiontransformer_b200/graph.py).  With N > 1 the NCCL gradient
+    # exchange and the optimizer run eagerly after the replay.
+    gstep = None
+    if use_graph:
+        from fusiontransformer_b200.fused import join_side_streams
+        from fusiontransformer_b200.graph import GraphedStep
+        if world == 1:
+            def body(plan):
+                loss = fwd_bwd(plan)
+                sync.finish()
+                opt.step()
+                return loss
+            gstep = GraphedStep(body, modules=[net])
+        else:
+            sync.deferred = True
+
+            def body(plan):
+                loss = fwd_bwd(plan)
+                join_side_streams()
+                return loss
+
+            def exchange_and_step():
+                sync.finish()
+                opt.step()
+            gstep = GraphedStep(body, modules=[net], after_replay=exchange_and_step)
+
+    cached_plans = {}
+    prepare = gstep.prepare if gstep is not None else dataflow.prepare_batch
+
+    def train_step(batch, nxt=None, eager=False):
+        t = time.perf_counter()
+        if args.reuse_plans:          # diagnostic: geometry of each distinct batch built once (not a valid bench mode)
+            plan = cached_plans.get(id(batch))
+            if plan is None:
+                plan = cached_plans[id(batch)] = dataflow.prepare_batch(batch, dev)
+            nxt = None
+        elif pre is None:
+            plan = dataflow.prepare_batch(batch, dev)
+        else:
+            if pre._pending is None:
+                pre.submit(dataflow.prepare_batch if eager else prepare, batch, dev)
+            plan = pre.get()
+        t = tick("get_plan", t)
+        if gstep is not None and not eager:
+            loss = gstep.step(plan)
+            t = tick("graph_step", t)
+        else:
+            loss = fwd_bwd(plan)
+            t = tick("forward_backward", t)
+            sync.finish()
+            opt.step()
+            t = tick("optimizer", t)
         if pre is not None and nxt is not None:
-            pre.submit(dataflow.prepare_batch, nxt, dev)
+            pre.submit(dataflow.prepare_batch if eager else prepare, nxt, dev)
         tick("prefetch_next", t)
         return loss
 
@@ -272,10 +320,13 @@ def main():
     # ---- device-resident timing (the `value`)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     L.calls.clear()
+    replays0 = gstep.replays if gstep is not None else 0
     ms = timed(lambda i: train_step(resident[i % nbatches], resident[(i + 1) % nbatches]), args.steps)
     if pre is not None and pre._pending is not None:
         pre.get()
     launches = _lib.launch_count(L.calls)
+    if gstep is not None:
+        launches += gstep.launches_per_replay * (gstep.replays - replays0)
     if diag is not None:
         print("host enqueue ms/step (device-resident loop): " +
               ", ".join("%s %.2f" % (k, 1e3 * v / (args.steps + args.warmup)) for k, v in diag.items()), file=sys.stderr)
@@ -307,8 +358,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for i in range(nprof):
-            train_step(resident[i % nbatches], resident[(i + 1) % nbatches])
+        for i in range(nprof):       # launched kernel by kernel (no graph replay) so that each entry point can be timed
+            train_step(resident[i % nbatches], resident[(i + 1) % nbatches], eager=True)
         e1.record()
         torch.cuda.synchronize()
         prof, work = L.profile, conv_engine.WORK_LOG
@@ -351,7 +402,7 @@ def main():
                         "tflops": fl / t_s / 1e12, "gbs": by / t_s / 1e9,
                         "share_of_step": tot[dom][0] / nprof / step_ms,
                         "note": "time = CUDA events around every conv_pairs_tc launch on the launching stream, "
-                                "summed over %d profiled steps" % nprof}
+                                "summed over %d separately profiled steps launched kernel by kernel" % nprof}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,7 +419,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if conv_engine.mode() == "tc" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "scans_per_gpu": B, "points_per_batch": nvox, "fusion": args.fusion,
                        "image_hw": [H, W], "parallelism": "dp%d" % world, "optimizer": "Adam(lr 1e-4, wd 5e-4)",
-                       "geometry_prefetch": bool(args.prefetch),
+                       "geometry_prefetch": bool(args.prefetch) and not args.reuse_plans,
+                       **({"INVALID_diagnostic": "geometry cached across steps"} if args.reuse_plans else {}),
+                       "cuda_graph": ("whole step, %d capture(s)" % gstep.captures) if gstep is not None else "off",
                        "linear_layers": "cuBLAS TF32" if conv_engine.mode() == "tc" else "cuBLAS fp32",
                        "l2": "no explicit flush: %d distinct batches are cycled and the step's working set (348 MB of "
                              "weights+Adam state, the activations and the %.1f GB feature map) exceeds the 126 MB L2"
@@ -379,6 +432,8 @@ def main():
             "kernel_ms_per_step": shares,
         }
         print(json.dumps(line), flush=True)
+    if pre is not None:
+        pre.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -105,12 +105,12 @@ def pairs_conv(x16, kmap, kernel, role: str):
     return ops.conv_reduce(partial, ppos, ncols)
 
 
-def pairs_wgrad(x16, g16, kmap, cin: int, cout: int, transpose: bool, into=None):
+def pairs_wgrad(x16, g16, kmap, cin: int, cout: int, transpose: bool, into=None, stream=None):
     L = kmap.num_pairs()
     if WORK_LOG is not None:
         WORK_LOG.append(dict(kind="conv_wgrad_pairs_tc", pairs=L, red=cin, ncols=cout, rows=L, K=kmap.K))
     return ops.conv_wgrad_pairs_tc(x16, g16, kmap.pairs_padded, kmap.pair_offsets, kmap.K, 1 if transpose else 0,
-                                   cin, cout, L, into=into)
+                                   cin, cout, L, into=into, stream=stream)
 
 
 def dense_conv(x16, kernel, w_transposed: bool):

@@ -30,8 +30,9 @@ __device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
 // ------------------------------------------------------------------------------------------------ statistics
 __global__ void __launch_bounds__(kColThreads)
 bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_per_cta,
-                float* __restrict__ partials) {
+                float* __restrict__ partials, const int32_t* __restrict__ valid_rows) {
   __shared__ float4 s_stage[kColStageFloat4];
+  n = effective_rows(n, valid_rows);
   const int ch = threadIdx.x * 4;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
@@ -49,12 +50,18 @@ bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_p
 __global__ void bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, const float* __restrict__ stat,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ res, int relu, float* __restrict__ z,
-                                __nv_bfloat16* __restrict__ z16) {
+                                __nv_bfloat16* __restrict__ z16, const int32_t* __restrict__ valid_rows) {
   const int cv = channels >> 2;
   const int64_t total = n * cv;
+  const int64_t nv = effective_rows(n, valid_rows);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = t / cv;
     const int ch = (int)(t - row * cv) << 2;
+    if (row >= nv) {                      // padding rows of a capacity-sized activation stay exactly zero
+      if (z != nullptr) *reinterpret_cast<float4*>(z + row * channels + ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (z16 != nullptr) *reinterpret_cast<uint2*>(z16 + row * channels + ch) = make_uint2(0u, 0u);
+      continue;
+    }
     const float4 v = ld4(y + row * channels + ch);
     const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), g = ld4(gamma + ch), b = ld4(beta + ch);
     float4 o;
@@ -91,8 +98,10 @@ __device__ __forceinline__ float4 masked_grad(const float* __restrict__ gz, cons
 __global__ void __launch_bounds__(kColThreads)
 bn_bwd_reduce_kernel(const float* __restrict__ gz, const float* __restrict__ y, const __nv_bfloat16* __restrict__ z16,
                      const float* __restrict__ z, int64_t n, int channels, int rows_per_cta,
-                     const float* __restrict__ stat, float* __restrict__ partials) {
+                     const float* __restrict__ stat, float* __restrict__ partials,
+                     const int32_t* __restrict__ valid_rows) {
   __shared__ float4 s_stage[kColStageFloat4];
+  n = effective_rows(n, valid_rows);
   const int ch = threadIdx.x * 4;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
@@ -114,13 +123,21 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ gz, const float* _
                                     const __nv_bfloat16* __restrict__ z16, const float* __restrict__ z, int64_t n,
                                     int channels, const float* __restrict__ stat, const float* __restrict__ gamma,
                                     const float* __restrict__ red, float* __restrict__ gy,
-                                    __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres) {
+                                    __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres,
+                                    const int32_t* __restrict__ valid_rows) {
   const int cv = channels >> 2;
   const int64_t total = n * cv;
+  const int64_t nv = effective_rows(n, valid_rows);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = t / cv;
     const int ch = (int)(t - row * cv) << 2;
     const int64_t off = row * channels + ch;
+    if (row >= nv) {                      // padding rows carry no gradient
+      if (gy != nullptr) *reinterpret_cast<float4*>(gy + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy16 != nullptr) *reinterpret_cast<uint2*>(gy16 + off) = make_uint2(0u, 0u);
+      if (gres != nullptr) *reinterpret_cast<float4*>(gres + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     const float4 g = masked_grad(gz, z16, z, off);
     const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), ga = ld4(gamma + ch);
     float4 o;
@@ -151,8 +168,8 @@ extern "C" {
 size_t ft3d_bn_workspace(int32_t channels) { return col_workspace_bytes(channels > 0 ? channels : 4); }
 
 int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float momentum, float* stat,
-                  float* running_mean, float* running_var, void* workspace, size_t workspace_bytes,
-                  ft3d_stream_t stream) {
+                  float* running_mean, float* running_var, const int32_t* valid_rows, void* workspace,
+                  size_t workspace_bytes, ft3d_stream_t stream) {
   FT3D_REQUIRE(n > 0, "ft3d_bn_stats: BatchNorm statistics need at least one row");
   FT3D_REQUIRE(y && stat && workspace && channels >= 4 && channels % 4 == 0 && channels <= 1024,
                "ft3d_bn_stats: bad arguments (channels=%d)", channels);
@@ -160,14 +177,16 @@ int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float 
   FT3D_REQUIRE(aligned16(y) && aligned16(workspace), "ft3d_bn_stats: pointers must be 16-byte aligned");
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_stats: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
-  bn_stats_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>(y, n, channels, g.rows_per_cta, (float*)workspace);
+  bn_stats_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>(y, n, channels, g.rows_per_cta, (float*)workspace,
+                                                                valid_rows);
   col_finalize_kernel<0><<<channels / 4, kColThreads, 0, (cudaStream_t)stream>>>(
-      (const float*)workspace, g.grid, channels, n, eps, momentum, stat, running_mean, running_var, 0);
+      (const float*)workspace, g.grid, channels, n, eps, momentum, stat, running_mean, running_var, 0, valid_rows);
   return check_launch("ft3d_bn_stats");
 }
 
 int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma, const float* beta,
-                  const float* res, int32_t relu, float* z, void* z16, ft3d_stream_t stream) {
+                  const float* res, int32_t relu, float* z, void* z16, const int32_t* valid_rows,
+                  ft3d_stream_t stream) {
   if (n == 0) return FT3D_OK;
   FT3D_REQUIRE(y && stat && gamma && beta && (z || z16) && channels >= 4 && channels % 4 == 0,
                "ft3d_bn_apply: bad arguments");
@@ -175,13 +194,13 @@ int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat
                    aligned16(z) && ((uintptr_t)z16 & 7) == 0,
                "ft3d_bn_apply: pointers must be 16-byte aligned");
   bn_apply_kernel<<<grid_for(n * (channels / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      y, n, channels, stat, gamma, beta, res, relu, z, (__nv_bfloat16*)z16);
+      y, n, channels, stat, gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows);
   return check_launch("ft3d_bn_apply");
 }
 
 int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const float* z, int64_t n, int32_t channels,
                        const float* stat, float* red, float* dgamma, float* dbeta, int32_t accumulate,
-                       void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
+                       const int32_t* valid_rows, void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
   FT3D_REQUIRE(n > 0, "ft3d_bn_bwd_reduce: needs at least one row");
   FT3D_REQUIRE(gz && y && stat && red && dgamma && dbeta && workspace && channels >= 4 &&
                    channels % 4 == 0 && channels <= 1024,
@@ -192,15 +211,15 @@ int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const f
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_bwd_reduce: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
   bn_bwd_reduce_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>(
-      gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace);
+      gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows);
   col_finalize_kernel<1><<<channels / 4, kColThreads, 0, (cudaStream_t)stream>>>(
-      (const float*)workspace, g.grid, channels, n, 0.f, 0.f, red, dgamma, dbeta, accumulate);
+      (const float*)workspace, g.grid, channels, n, 0.f, 0.f, red, dgamma, dbeta, accumulate, valid_rows);
   return check_launch("ft3d_bn_bwd_reduce");
 }
 
 int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const float* z, int64_t n, int32_t channels,
                       const float* stat, const float* gamma, const float* red, float* gy, void* gy16, float* gres,
-                      ft3d_stream_t stream) {
+                      const int32_t* valid_rows, ft3d_stream_t stream) {
   if (n == 0) return FT3D_OK;
   FT3D_REQUIRE(gz && stat && gamma && (y || !red) && (gy || gy16 || gres) && channels >= 4 && channels % 4 == 0,
                "ft3d_bn_bwd_apply: bad arguments");
@@ -208,7 +227,7 @@ int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const fl
                    aligned16(gamma) && aligned16(red) && aligned16(gy) && ((uintptr_t)gy16 & 7) == 0 && aligned16(gres),
                "ft3d_bn_bwd_apply: pointers must be 16-byte aligned");
   bn_bwd_apply_kernel<<<grid_for(n * (channels / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      gz, y, (const __nv_bfloat16*)z16, z, n, channels, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres);
+      gz, y, (const __nv_bfloat16*)z16, z, n, channels, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows);
   return check_launch("ft3d_bn_bwd_apply");
 }
 

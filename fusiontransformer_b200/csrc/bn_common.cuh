@@ -43,6 +43,14 @@ static inline size_t col_workspace_bytes(int channels) {
   return align_up((size_t)kColMaxCtas * 2 * channels * sizeof(float), 256);
 }
 
+// Row count of a capacity-padded activation: the launch covers `n` rows, of which the first *valid_rows are real
+// (CUDA-graph replay with static shapes, graph.py).  valid_rows == nullptr: all n rows are real.
+__device__ __forceinline__ int64_t effective_rows(int64_t n, const int32_t* __restrict__ valid_rows) {
+  if (valid_rows == nullptr) return n;
+  const int64_t v = (int64_t)__ldg(valid_rows);
+  return v < n ? v : n;
+}
+
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 __device__ __forceinline__ void fma4(float4& a, const float4& b, const float4& c) {
   a.x = fmaf(b.x, c.x, a.x); a.y = fmaf(b.y, c.y, a.y); a.z = fmaf(b.z, c.z, a.z); a.w = fmaf(b.w, c.w, a.w);
@@ -78,8 +86,11 @@ __device__ __forceinline__ void col_publish(float4 s1, float4 s2, float* __restr
 template <int MODE>
 __global__ void __launch_bounds__(kColThreads)
 col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels, int64_t n, float eps, float momentum,
-                    float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2, int accumulate) {
+                    float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2, int accumulate,
+                    const int32_t* __restrict__ valid_rows) {
   __shared__ double s_acc[kColThreads][8];
+  n = effective_rows(n, valid_rows);
+  if (n < 1) n = 1;
   const int t = threadIdx.x, c0 = blockIdx.x * 4;
   double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int b = t; b < nparts; b += kColThreads) {

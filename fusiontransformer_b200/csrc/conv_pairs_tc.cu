@@ -469,8 +469,8 @@ int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t*
 
 static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
                          float* out, bool stats, float eps, float momentum, float* stat, float* running_mean,
-                         float* running_var, void* workspace, size_t workspace_bytes, cudaStream_t s,
-                         const char* what) {
+                         float* running_var, const int32_t* valid_rows, void* workspace, size_t workspace_bytes,
+                         cudaStream_t s, const char* what) {
   FT3D_REQUIRE(ppos && out && (kpad == 8 || kpad == 16 || kpad == 32) && ncols >= 4 && ncols % 4 == 0 && ncols <= 1024,
                "%s: bad arguments", what);
   FT3D_REQUIRE(((uintptr_t)partial & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)ppos & 15) == 0,
@@ -483,7 +483,7 @@ static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_ro
     conv_reduce_kernel<true><<<g.grid, g.block, 0, s>>>(partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
                                                         (float*)workspace);
     col_finalize_kernel<0><<<ncols / 4, kColThreads, 0, s>>>((const float*)workspace, g.grid, ncols, n_rows, eps, momentum,
-                                                             stat, running_mean, running_var, 0);
+                                                             stat, running_mean, running_var, 0, valid_rows);
   } else {
     conv_reduce_kernel<false><<<g.grid, g.block, 0, s>>>(partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr);
   }
@@ -493,16 +493,16 @@ static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_ro
 int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
                      float* out, ft3d_stream_t stream) {
   if (n_rows == 0) return FT3D_OK;
-  return launch_reduce(partial, ppos, n_rows, kpad, ncols, out, false, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
-                       (cudaStream_t)stream, "ft3d_conv_reduce");
+  return launch_reduce(partial, ppos, n_rows, kpad, ncols, out, false, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, 0, (cudaStream_t)stream, "ft3d_conv_reduce");
 }
 
 int ft3d_conv_reduce_bn(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
                         float* out, float eps, float momentum, float* stat, float* running_mean, float* running_var,
-                        void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
+                        const int32_t* valid_rows, void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
   FT3D_REQUIRE(n_rows > 0, "ft3d_conv_reduce_bn: BatchNorm statistics need at least one row");
   return launch_reduce(partial, ppos, n_rows, kpad, ncols, out, true, eps, momentum, stat, running_mean, running_var,
-                       workspace, workspace_bytes, (cudaStream_t)stream, "ft3d_conv_reduce_bn");
+                       valid_rows, workspace, workspace_bytes, (cudaStream_t)stream, "ft3d_conv_reduce_bn");
 }
 
 int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32_t* pairs,

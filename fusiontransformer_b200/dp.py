@@ -15,7 +15,10 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20, process_group=None, overlap: bool = True):
+    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20, process_group=None, overlap: bool = True,
+                 side_wgrad: bool = True):
+        self.side_wgrad = side_wgrad       # fused.py: weight-gradient kernels run on a second stream
+        self.deferred = False              # True: hooks do nothing, finish() exchanges every bucket (graph replay)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.params = [p for p in module.parameters() if p.requires_grad]
@@ -61,6 +64,11 @@ class GradSync:
         if self.world > 1:
             self._hook(p)
 
+    @staticmethod
+    def _join_side():
+        from .fused import join_side_streams
+        join_side_streams()
+
     # -- broadcast initial parameters/buffers from rank 0 (what DDP's constructor does)
     def broadcast_parameters(self, module: torch.nn.Module):
         if self.world == 1:
@@ -77,6 +85,7 @@ class GradSync:
         if self._launched[b]:
             return
         self._launched[b] = True
+        self._join_side()                   # side-stream wgrad kernels of this bucket must have been ordered first
         s, e = self.buckets[b]
         view = self.flat[s:e]
         if self.overlap:
@@ -87,6 +96,8 @@ class GradSync:
             self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _hook(self, p):
+        if self.deferred:
+            return
         b = self._bucket_of[p]
         self._seen[b] += 1
         if self._seen[b] == self._need[b]:
@@ -94,6 +105,7 @@ class GradSync:
 
     def finish(self):
         """Call after backward: launches buckets with unused parameters, waits, and averages over ranks."""
+        self._join_side()
         if self.world == 1:
             return
         for b in range(len(self.buckets)):

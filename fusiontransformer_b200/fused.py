@@ -27,7 +27,39 @@ from . import nn as spnn
 from .functional import conv_geometry
 from .sparse_tensor import SparseTensor
 
-__all__ = ["conv_bn_act", "fuse", "unfuse"]
+__all__ = ["conv_bn_act", "fuse", "unfuse", "join_side_streams"]
+
+
+class _SideStream:
+    """wgrad runs on a second stream: it only feeds the optimizer, so it need not sit on the dgrad critical path of
+    the backward pass.  One side stream per device; ``join()`` (called by dp.GradSync before it reads gradients)
+    makes the main stream wait for everything queued on it.  Operand tensors are kept referenced until the join, so
+    the caching allocator cannot hand their memory to a main-stream kernel that runs before the wgrad has read it
+    (cheaper than record_stream, and legal under CUDA-graph capture)."""
+    streams = {}
+    keep = []
+    dirty = set()
+
+    @classmethod
+    def fork(cls, device):
+        """-> raw cudaStream_t of the side stream, ordered after everything queued on the current stream so far."""
+        st = cls.streams.get(device.index)
+        if st is None:
+            st = cls.streams[device.index] = torch.cuda.Stream(device=device)
+        st.wait_stream(torch.cuda.current_stream(device))
+        cls.dirty.add(device.index)
+        return st.cuda_stream
+
+    @classmethod
+    def join(cls):
+        for idx in list(cls.dirty):
+            torch.cuda.current_stream(idx).wait_stream(cls.streams[idx])
+        cls.dirty.clear()
+        cls.keep.clear()
+
+
+def join_side_streams():
+    _SideStream.join()
 
 
 def _role(transpose: bool, grad: bool) -> str:
@@ -115,7 +147,13 @@ class _ConvBNAct(torch.autograd.Function):
             else:
                 if need_in:
                     gin = conv_engine.pairs_conv(gy16, kmap, kernel, _role(transpose, True))
-                if need_w:
+                if need_w and sink is not None and sink.side_wgrad:
+                    # gradient goes straight into the arena, nothing downstream in autograd consumes it: run it
+                    # beside the dgrad chain
+                    raw = _SideStream.fork(gz.device)
+                    conv_engine.pairs_wgrad(saved_in, gy16, kmap, cin, cout, transpose, into=kernel.grad, stream=raw)
+                    _SideStream.keep.append((saved_in, gy16))
+                elif need_w:
                     gw = conv_engine.pairs_wgrad(saved_in, gy16, kmap, cin, cout, transpose,
                                                  into=kernel.grad if sink else None)
             if sink is not None and need_w:
@@ -142,6 +180,54 @@ class _ConvBNAct(torch.autograd.Function):
             sink.note(gamma)
             sink.note(beta)
         return gin, gw, dgamma, dbeta, gres, None, None, None, None, None
+
+
+class _BNAct(torch.autograd.Function):
+    """``relu?(batch_norm(y))`` on a plain [N,C] tensor: the point-branch ``Linear -> BatchNorm1d -> ReLU`` blocks
+    (models/spvcnn.py:164-180, middle_fusion.py:18-22) on the same kernels as the voxel branch."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, relu, bn):
+        training = bn.training or bn.running_mean is None
+        rm, rv = (bn.running_mean, bn.running_var) if (bn.training and bn.track_running_stats) else (None, None)
+        y = y.contiguous()
+        if training:
+            stat = ops.bn_stats(y, bn.eps, bn.momentum, rm, rv)
+        else:
+            stat = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)]).contiguous()
+        z, _ = ops.bn_apply(y, stat, gamma, beta, None, relu, want_f32=True, want_bf16=False)
+        ctx.training, ctx.beta = training, beta
+        ctx.save_for_backward(y, gamma, stat, z if relu else None)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        y, gamma, stat, mask = ctx.saved_tensors
+        beta = ctx.beta
+        gz = gz.contiguous()
+        sink = getattr(gamma, "_ft3d_sink", None)
+        if sink is not None and not (sink.owns(gamma) and sink.owns(beta)):
+            sink = None
+        if sink is not None:
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat, gamma.grad, beta.grad)
+            sink.note(gamma)
+            sink.note(beta)
+        else:
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat)
+        gy, _, _ = ops.bn_bwd_apply(gz, y, None, mask, stat, gamma, red if ctx.training else None,
+                                    want_f32=True, want_bf16=False, want_res=False)
+        return gy, dgamma, dbeta, None, None
+
+
+def bn_act(y: torch.Tensor, bn, relu: bool) -> torch.Tensor:
+    out = _BNAct.apply(y, bn.weight, bn.bias, relu, bn)
+    if bn.training and bn.track_running_stats:
+        bn._ft3d_pending_batches = getattr(bn, "_ft3d_pending_batches", 0) + 1
+    return out
+
+
+def _bn1d_fusable(bn) -> bool:
+    return (type(bn) is nn.BatchNorm1d and bn.affine and bn.momentum is not None and bn.num_features % 4 == 0)
 
 
 def _fusable(conv, bn) -> bool:
@@ -185,6 +271,11 @@ def _sequential_forward(self, x):
             relu = i + 2 < n and type(mods[i + 2]) is spnn.ReLU
             x = conv_bn_act(x, m, mods[i + 1], relu)
             i += 3 if relu else 2
+        elif (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+              and _bn1d_fusable(m)):
+            relu = i + 1 < n and type(mods[i + 1]) is nn.ReLU
+            x = bn_act(x, m, relu)
+            i += 2 if relu else 1
         else:
             x = m(x)
             i += 1
@@ -220,7 +311,7 @@ def fuse(model: nn.Module) -> nn.Module:
             m._ft3d_fused = True
         elif isinstance(m, nn.Sequential):
             mods = list(m)
-            if any(_fusable(a, b) for a, b in zip(mods, mods[1:])):
+            if any(_fusable(a, b) for a, b in zip(mods, mods[1:])) or any(_bn1d_fusable(a) for a in mods):
                 m.forward = types.MethodType(_sequential_forward, m)
                 m._ft3d_fused = True
         if isinstance(m, nn.BatchNorm1d) and not getattr(m, "_ft3d_hooked", False):

@@ -327,6 +327,7 @@ def conv_wgrad_f32(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
 
 
 _PACK_CACHE = {}
+FORCE_REPACK = False     # graph.py sets this while capturing: the pack launch must be part of every replay
 
 
 def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Tensor:
@@ -338,7 +339,8 @@ def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Ten
     owner = w if owner is None else owner
     key = (id(owner), bool(w_transposed))
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0]() is owner and hit[1] == owner._version and hit[2] == w.data_ptr():
+    if (not FORCE_REPACK and hit is not None and hit[0]() is owner and hit[1] == owner._version
+            and hit[2] == w.data_ptr()):
         return hit[3]
     k, cin, cout = w.shape
     red, ncols = (cout, cin) if w_transposed else (cin, cout)
@@ -408,6 +410,16 @@ def conv_reduce(partial, ppos, ncols):
 
 
 # ----------------------------------------------------------------------------- fused BatchNorm / ReLU / residual
+# Static-shape execution (graph.py): activations are padded to a capacity; the number of real rows of every padded
+# row dimension lives in a device int32 and is looked up here by that dimension (capacities are made distinct).
+ROW_COUNTS = {}
+
+
+def _valid(n_rows: int) -> int:
+    t = ROW_COUNTS.get(n_rows)
+    return 0 if t is None else t.data_ptr()
+
+
 _BN_SCRATCH = {}
 
 
@@ -430,8 +442,8 @@ def conv_reduce_bn(partial, ppos, ncols, eps, momentum, running_mean, running_va
     stat = torch.empty((2, ncols), dtype=torch.float32, device=dev)
     ws = bn_scratch(dev)
     lib().conv_reduce_bn(partial.data_ptr(), ppos.data_ptr(), n_rows, kpad, ncols, out.data_ptr(), float(eps),
-                         float(momentum), stat.data_ptr(), _p(running_mean), _p(running_var), ws.data_ptr(), ws.numel(),
-                         _stream())
+                         float(momentum), stat.data_ptr(), _p(running_mean), _p(running_var), _valid(n_rows),
+                         ws.data_ptr(), ws.numel(), _stream())
     return out, stat
 
 
@@ -440,7 +452,7 @@ def bn_stats(y, eps, momentum, running_mean, running_var):
     stat = torch.empty((2, c), dtype=torch.float32, device=y.device)
     ws = bn_scratch(y.device)
     lib().bn_stats(y.data_ptr(), n, c, float(eps), float(momentum), stat.data_ptr(), _p(running_mean), _p(running_var),
-                   ws.data_ptr(), ws.numel(), _stream())
+                   _valid(n), ws.data_ptr(), ws.numel(), _stream())
     return stat
 
 
@@ -449,7 +461,7 @@ def bn_apply(y, stat, gamma, beta, res, relu: bool, want_f32: bool = True, want_
     z = torch.empty((n, c), dtype=torch.float32, device=y.device) if want_f32 else None
     z16 = torch.empty((n, c), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
     lib().bn_apply(y.data_ptr(), n, c, stat.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(res), int(relu), _p(z),
-                   _p(z16), _stream())
+                   _p(z16), _valid(n), _stream())
     return z, z16
 
 
@@ -462,11 +474,12 @@ def bn_bwd_reduce(gz, y, z16, z, stat, dgamma_into=None, dbeta_into=None):
     ws = bn_scratch(dev)
     if dgamma_into is not None:
         lib().bn_bwd_reduce(gz.data_ptr(), y.data_ptr(), _p(z16), _p(z), n, c, stat.data_ptr(), red.data_ptr(),
-                            dgamma_into.data_ptr(), dbeta_into.data_ptr(), 1, ws.data_ptr(), ws.numel(), _stream())
+                            dgamma_into.data_ptr(), dbeta_into.data_ptr(), 1, _valid(n), ws.data_ptr(), ws.numel(),
+                            _stream())
         return red, None, None
     dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
     lib().bn_bwd_reduce(gz.data_ptr(), y.data_ptr(), _p(z16), _p(z), n, c, stat.data_ptr(), red.data_ptr(),
-                        dgb[0].data_ptr(), dgb[1].data_ptr(), 0, ws.data_ptr(), ws.numel(), _stream())
+                        dgb[0].data_ptr(), dgb[1].data_ptr(), 0, _valid(n), ws.data_ptr(), ws.numel(), _stream())
     return red, dgb[0], dgb[1]
 
 
@@ -477,16 +490,16 @@ def bn_bwd_apply(gz, y, z16, z, stat, gamma, red, want_f32: bool, want_bf16: boo
     gy16 = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if want_bf16 else None
     gres = torch.empty((n, c), dtype=torch.float32, device=dev) if want_res else None
     lib().bn_bwd_apply(gz.data_ptr(), _p(y), _p(z16), _p(z), n, c, stat.data_ptr(), gamma.data_ptr(), _p(red), _p(gy),
-                       _p(gy16), _p(gres), _stream())
+                       _p(gy16), _p(gres), _valid(n), _stream())
     return gy, gy16, gres
 
 
-def conv_wgrad_pairs_tc(a16, b16, pairs, offsets, k, ca, cin, cout, max_pairs, into=None):
+def conv_wgrad_pairs_tc(a16, b16, pairs, offsets, k, ca, cin, cout, max_pairs, into=None, stream=None):
     """``into``: an fp32 tensor of k*cin*cout elements that the gradient is ACCUMULATED into (the kernel adds with
     atomics anyway); otherwise a fresh zero-filled tensor is returned."""
     a16 = _chk(a16, torch.bfloat16, "a16")
     b16 = _chk(b16, torch.bfloat16, "b16")
     gw = into if into is not None else torch.zeros((k, cin, cout), dtype=torch.float32, device=a16.device)
     lib().conv_wgrad_pairs_tc(a16.data_ptr(), b16.data_ptr(), _p(pairs), _p(offsets), k, int(ca), cin, cout,
-                              int(max_pairs), gw.data_ptr(), _stream())
+                              int(max_pairs), gw.data_ptr(), _stream() if stream is None else stream)
     return gw

@@ -102,27 +102,62 @@ def build_plan(coords: torch.Tensor, strides=(1, 2, 4, 8, 16), v2p_strides=(1, 1
 
 
 class Prefetcher:
-    """Runs ``fn(*args)`` (batch upload + voxelization + build_plan) on a high-priority side stream.
+    """Runs ``fn(*args)`` (batch upload + voxelization + build_plan) on a high-priority side stream, from a worker
+    thread: the ~15 host reads of data-dependent sizes block that thread (GIL released), not the thread that is
+    enqueueing the current step's convolutions.
 
-    ``submit`` enqueues the work for the NEXT step (its host reads wait only for the side stream); ``get`` makes the
-    consumer's stream wait for it and tells the caching allocator which stream now uses the tensors."""
+    ``submit`` queues the work for the NEXT step; ``get`` waits for the worker, makes the consumer's stream wait for
+    the side stream and tells the caching allocator which stream now uses the tensors."""
 
-    def __init__(self, device=None):
-        self.stream = torch.cuda.Stream(device=device, priority=-1)
+    def __init__(self, device=None, threaded: bool = True):
+        import queue
+        import threading
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._pending = None
+        self._threaded = threaded
+        if threaded:
+            self._jobs, self._done = queue.Queue(), queue.Queue()
+            self._worker = threading.Thread(target=self._loop, name="ft3d-prefetch", daemon=True)
+            self._worker.start()
+
+    def _run(self, fn, args):
+        with torch.cuda.stream(self.stream):
+            out = fn(*args)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return out, ev
+
+    def _loop(self):
+        torch.cuda.set_device(self.device)
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            try:
+                self._done.put((self._run(*job), None))
+            except BaseException as e:  # noqa: BLE001 -- re-raised in get()
+                self._done.put((None, e))
 
     def submit(self, fn, *args):
         assert self._pending is None, "one batch in flight"
         # NB no wait on the consumer's stream: fn's inputs must already be complete (resident batches, or pinned host
         # memory that fn uploads itself) -- waiting would chain the plan's host reads behind the running step.
-        with torch.cuda.stream(self.stream):
-            out = fn(*args)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self._pending = (out, ev)
+        if self._threaded:
+            self._jobs.put((fn, args))
+            self._pending = "queued"
+        else:
+            self._pending = self._run(fn, args)
 
     def get(self):
-        out, ev = self._pending
+        if self._threaded:
+            res, err = self._done.get()
+            if err is not None:
+                self._pending = None
+                raise err
+            out, ev = res
+        else:
+            out, ev = self._pending
         self._pending = None
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
@@ -132,3 +167,8 @@ class Prefetcher:
             elif isinstance(o, torch.Tensor):
                 o.record_stream(cur)
         return out
+
+    def close(self):
+        if self._threaded and self._worker.is_alive():
+            self._jobs.put(None)
+            self._worker.join(timeout=5)

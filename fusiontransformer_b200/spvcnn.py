@@ -162,6 +162,9 @@ class Net3DSeg(SPVCNN):
         self.dual_head = dual_head
         if dual_head:
             self.linear2 = nn.Linear(self.cs[-1], num_classes)
+        if os.environ.get("FT3D_FUSE", "1") != "0":
+            from .fused import fuse
+            fuse(self)                      # the fusion MLP added above
 
     def forward(self, x, img_feats=None, taps=None, plan=None):
         early = middle = None

@@ -193,7 +193,8 @@ int ft3d_conv_reduce(const float* partial, const int32_t* ppos, int64_t n_rows, 
                      float* out, ft3d_stream_t stream);
 int ft3d_conv_reduce_bn(const float* partial, const int32_t* ppos, int64_t n_rows, int32_t kpad, int32_t ncols,
                         float* out, float eps, float momentum, float* stat, float* running_mean,
-                        float* running_var, void* workspace, size_t workspace_bytes, ft3d_stream_t stream);
+                        float* running_var, const int32_t* valid_rows, void* workspace, size_t workspace_bytes,
+                        ft3d_stream_t stream);
 /* wgrad on bf16 inputs: gw[k] += a_bf16[pairs[p][ca],:]^T b_bf16[pairs[p][1-ca],:]; pairs == NULL: identity (K == 1). */
 int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32_t* pairs,
                              const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin, int32_t cout,
@@ -204,26 +205,31 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
 /* Column reductions are deterministic: per-CTA partial rows in `workspace` (ft3d_bn_workspace(C) bytes), folded in
  * double by a second tiny launch with a fixed-shape tree; no float atomics.  stat f32 [2,C] = (batch mean,
  * 1/sqrt(biased var + eps)); running_mean/var (nullable pair) are updated with `momentum` and the unbiased variance
- * exactly as nn.BatchNorm1d does in training mode. */
+ * exactly as nn.BatchNorm1d does in training mode.
+ * valid_rows (nullable, device int32): the activation is padded to a static capacity of n rows of which only the
+ * first *valid_rows are real -- statistics divide by that count and the apply kernels keep the padding rows exactly
+ * zero, so a whole training step can be replayed as one CUDA graph for batches of different size (graph.py). */
 size_t ft3d_bn_workspace(int32_t channels);
 int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float momentum, float* stat,
-                  float* running_mean, float* running_var, void* workspace, size_t workspace_bytes,
-                  ft3d_stream_t stream);
+                  float* running_mean, float* running_var, const int32_t* valid_rows, void* workspace,
+                  size_t workspace_bytes, ft3d_stream_t stream);
 /* z = [relu]((y - mean) * rstd * gamma + beta [+ res]); writes z f32 [n,C] (nullable) and z16 bf16 [n,C]
  * (nullable) -- the copy the next convolution gathers.  Evaluation mode: pass stat built from the running stats. */
 int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma,
-                  const float* beta, const float* res, int32_t relu, float* z, void* z16, ft3d_stream_t stream);
+                  const float* beta, const float* res, int32_t relu, float* z, void* z16,
+                  const int32_t* valid_rows, ft3d_stream_t stream);
 /* g' = gz * [z > 0] (mask from z16 if given, else z, else none).  red f32 [2,C] = (sum g'/n, sum g' xhat/n);
  * dgamma = sum g' xhat; dbeta = sum g' (accumulate != 0: added to the values already there, so the gradients can
  * be written straight into a flat gradient arena). */
 int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const float* z, int64_t n,
                        int32_t channels, const float* stat, float* red, float* dgamma, float* dbeta,
-                       int32_t accumulate, void* workspace, size_t workspace_bytes, ft3d_stream_t stream);
+                       int32_t accumulate, const int32_t* valid_rows, void* workspace, size_t workspace_bytes,
+                       ft3d_stream_t stream);
 /* gy = gamma rstd (g' - c1 - xhat c2)  (red == NULL: frozen statistics, gy = gamma rstd g'); outputs (each
  * nullable): gy f32, gy16 bf16 (the dgrad / wgrad operand), gres f32 = g' (gradient of the residual input). */
 int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const float* z, int64_t n,
                       int32_t channels, const float* stat, const float* gamma, const float* red, float* gy,
-                      void* gy16, float* gres, ft3d_stream_t stream);
+                      void* gy16, float* gres, const int32_t* valid_rows, ft3d_stream_t stream);
 
 #ifdef __cplusplus
 }
