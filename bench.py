@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel of the step from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--reuse-plans", action="store_true", help="diagnostic only: time the compute with cached geometry")
+    ap.add_argument("--trace", type=int, default=0, metavar="N",
+                    help="after the timed runs, profile N more steps with torch.profiler and print the GPU kernel table")
     ap.add_argument("--diag", action="store_true", help="print host-side enqueue time per phase (stderr)")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="build each batch's geometry inside its own step (host reads stall the launch queue)")
@@ -403,6 +405,30 @@ def main():
                         "share_of_step": tot[dom][0] / nprof / step_ms,
                         "note": "time = CUDA events around every conv_pairs_tc launch on the launching stream, "
                                 "summed over %d separately profiled steps launched kernel by kernel" % nprof}
+
+    if args.trace and rank == 0:
+        from torch.autograd import DeviceType
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for i in range(args.trace):
+                train_step(resident[i % nbatches], resident[(i + 1) % nbatches])
+            torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / args.trace * 1e3
+        agg, t_lo, t_hi = {}, None, None
+        for e in prof.events():
+            if e.device_type == DeviceType.CUDA:
+                a = agg.setdefault(e.name, [0.0, 0])
+                a[0] += e.device_time_total
+                a[1] += 1
+        rows = sorted(((v[0] / args.trace / 1e3, v[1] / args.trace, k) for k, v in agg.items()), reverse=True)
+        print("trace: wall %.2f ms/step under profiler, sum of GPU kernel time %.2f ms/step, %d launches/step"
+              % (wall, sum(r[0] for r in rows), sum(r[1] for r in rows)), file=sys.stderr)
+        for ms_, cnt, key in rows[:40]:
+            print("  %8.3f ms %6.1f x  %s" % (ms_, cnt, key[:120]), file=sys.stderr)
+        if pre is not None and pre._pending is not None:
+            pre.get()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

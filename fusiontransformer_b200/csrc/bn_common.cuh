@@ -93,12 +93,24 @@ col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels
   if (n < 1) n = 1;
   const int t = threadIdx.x, c0 = blockIdx.x * 4;
   double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int b = t; b < nparts; b += kColThreads) {
-    const float* p = partials + (size_t)b * 2 * channels + c0;
-    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p + channels));
-    a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
-    a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+  // up to 4 partial rows per thread are requested before the first add: one L2 round trip for <= 1024 CTAs
+  for (int b0 = t; b0 < nparts; b0 += 4 * kColThreads) {
+    float4 u[4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b0 + i * kColThreads;
+      u[i] = v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < nparts) {
+        const float* p = partials + (size_t)b * 2 * channels + c0;
+        u[i] = __ldg(reinterpret_cast<const float4*>(p));
+        v[i] = __ldg(reinterpret_cast<const float4*>(p + channels));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[0] += u[i].x; a[1] += u[i].y; a[2] += u[i].z; a[3] += u[i].w;
+      a[4] += v[i].x; a[5] += v[i].y; a[6] += v[i].z; a[7] += v[i].w;
+    }
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) s_acc[t][e] = a[e];

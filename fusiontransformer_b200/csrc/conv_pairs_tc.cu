@@ -84,7 +84,9 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
   const int nkb = (red + 63) / 64;
   const int b_bytes = ncols * kBlockRowBytes;
   const int stage_bytes = kBlockBytes + b_bytes;
-  PairsSmemHeader* hdr = (PairsSmemHeader*)(smem + (size_t)nstages * stage_bytes);   // ring: nstages <= nkb
+  const int staging_bytes = kTileRows * (ncols + 4) * (int)sizeof(float);
+  const int ring_bytes = nstages * stage_bytes > staging_bytes ? nstages * stage_bytes : staging_bytes;
+  PairsSmemHeader* hdr = (PairsSmemHeader*)(smem + (size_t)((ring_bytes + 127) & ~127));   // ring: nstages <= nkb
 
   int k = 0, begin, end;
   if (pairs != nullptr) {
@@ -133,21 +135,29 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
       gather_block_bf16(smem + (size_t)s * stage_bytes, in, red, kb * 64, width >> 3, tid, hdr->idx);
       cp_async_arrive_noinc(&hdr->full[s]);
     }
-    // epilogue: TMEM lane = pair row of the tile
+    // epilogue: TMEM lane = pair row of the tile.  Each thread stages its row in shared memory (the operand stages
+    // are free once accum_full has fired; rows padded by 16 B so that the 8 lanes of a quarter-warp hit 8 different
+    // bank groups) and hands it to the TMA unit as ONE bulk store: the P row is ncols*4 contiguous bytes in global
+    // memory, written as full sectors instead of 32 scattered 16-byte pieces per warp instruction.
     mbar_wait(&hdr->accum_full, 0);
     tc_fence_after();
     const int p = begin + tid;
-    float* prow = P + (int64_t)p * ncols;
+    const int row_floats = ncols + 4;
+    float* srow = reinterpret_cast<float*>(smem) + (size_t)tid * row_floats;
     for (int c0 = 0; c0 < ncols; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (p < end) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-      }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(srow + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    if (p < end) {
+      fence_proxy_async_smem();            // this thread's st.shared -> visible to the bulk-copy (async proxy) read
+      bulk_s2g(P + (int64_t)p * ncols, srow, (uint32_t)ncols * 4u);
+      bulk_commit_group();
+      bulk_wait_group_read0();             // shared memory must stay intact until the copy engine has read it
     }
   } else if (warp == 4) {
     if (lane == 0) {
@@ -450,11 +460,14 @@ int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t*
                "ft3d_conv_pairs_tc: pointers must be 16-byte aligned");
   const int nkb = (red + 63) / 64;
   const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes;
-  const int tail = (int)sizeof(PairsSmemHeader) + 1024;
+  const int tail = (int)sizeof(PairsSmemHeader) + 1024 + 128;
   int nstages = (226 * 1024 - tail) / stage_bytes;
   if (nstages > nkb) nstages = nkb;
   FT3D_REQUIRE(nstages >= 1, "ft3d_conv_pairs_tc: red=%d ncols=%d does not fit shared memory", red, ncols);
-  const int smem_bytes = nstages * stage_bytes + tail;
+  const int staging = tc::kTileRows * (ncols + 4) * (int)sizeof(float);     // epilogue rows reuse the operand stages
+  const int ring = nstages * stage_bytes > staging ? nstages * stage_bytes : staging;
+  FT3D_REQUIRE(ring + tail <= 227 * 1024, "ft3d_conv_pairs_tc: ncols=%d does not fit shared memory", ncols);
+  const int smem_bytes = ring + tail;
   static int configured = 0;
   if (!configured) {
     FT3D_CUDA(cudaFuncSetAttribute(conv_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
