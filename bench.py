@@ -222,7 +222,8 @@ def main():
     # The geometry of batch i+1 (upload, voxelization, kernel maps: every host read of a data-dependent size) is
     # built on a high-priority side stream while batch i's convolutions run (fusiontransformer_b200/plan.py).
     from fusiontransformer_b200.plan import Prefetcher
-    pre = Prefetcher(dev, threaded=not args.no_prefetch_thread) if args.prefetch else None
+    pre = Prefetcher(dev, threaded=not args.no_prefetch_thread,
+                     priority=int(os.environ.get("FT3D_PREFETCH_PRIORITY", "-1"))) if args.prefetch else None
 
     diag = {} if args.diag else None
 
@@ -231,10 +232,15 @@ def main():
             diag[name] = diag.get(name, 0.0) + (time.perf_counter() - t0)
         return time.perf_counter()
 
+    from fusiontransformer_b200.fused import weight_packer
+    packer = weight_packer(net) if conv_engine.mode() == "tc" else None
+
     def fwd_bwd(plan):
+        if packer is not None:
+            packer.pack()                 # all 96 bf16 weight images (the optimizer moved the weights) in one launch
         ex = plan.extras
         img = ft.nn.functional.lift(fmap, ex["rc"], ex["bidx"]) if args.fusion != "none" else None
-        out = net(ex["lidar"], None if img is None else img.detach())
+        out = net(ex["lidar"], None if img is None else img.detach(), plan=plan)
         loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], ex["labels"])
         sync.zero_grad()
         loss.backward()
@@ -303,12 +309,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_wall = []
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
+            tw = time.perf_counter()
             fn(i)
+            step_wall.append(1e3 * (time.perf_counter() - tw))
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -332,6 +342,8 @@ def main():
     if diag is not None:
         print("host enqueue ms/step (device-resident loop): " +
               ", ".join("%s %.2f" % (k, 1e3 * v / (args.steps + args.warmup)) for k, v in diag.items()), file=sys.stderr)
+        print("host ms per step: " + " ".join("%.1f" % v for v in step_wall), file=sys.stderr)
+        step_wall.clear()
         diag.clear()
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
@@ -353,7 +365,7 @@ def main():
 
     # ---- per-entry-point device times + conv work log (separate pass, not part of the reported value)
     roofline, shares = None, None
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:             # every rank runs the pass (the steps contain collectives); rank 0 reports
         pk = peaks()
         L.profile, conv_engine.WORK_LOG = [], []
         nprof = min(args.steps, 5)
@@ -406,7 +418,7 @@ def main():
                         "note": "time = CUDA events around every conv_pairs_tc launch on the launching stream, "
                                 "summed over %d separately profiled steps launched kernel by kernel" % nprof}
 
-    if args.trace and rank == 0:
+    if args.trace and world == 1:
         from torch.autograd import DeviceType
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()

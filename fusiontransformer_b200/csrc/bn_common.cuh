@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kColThreads)
 col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels, int64_t n, float eps, float momentum,
                     float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2, int accumulate,
                     const int32_t* __restrict__ valid_rows) {
-  __shared__ double s_acc[kColThreads][8];
+  __shared__ double s_acc[kColThreads / 32][8];
   n = effective_rows(n, valid_rows);
   if (n < 1) n = 1;
   const int t = threadIdx.x, c0 = blockIdx.x * 4;
@@ -112,16 +112,23 @@ col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels
       a[4] += v[i].x; a[5] += v[i].y; a[6] += v[i].z; a[7] += v[i].w;
     }
   }
+  // fixed-shape fold: xor-butterfly inside each warp (no barrier), then the 8 warp totals through shared memory
 #pragma unroll
-  for (int e = 0; e < 8; ++e) s_acc[t][e] = a[e];
-  __syncthreads();
-  for (int stride = kColThreads / 2; stride >= 1; stride >>= 1) {
-    if (t < stride) {
+  for (int e = 0; e < 8; ++e) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s_acc[t][e] += s_acc[t + stride][e];
-    }
-    __syncthreads();
+    for (int o = 16; o >= 1; o >>= 1) a[e] += __shfl_xor_sync(0xffffffffu, a[e], o);
   }
+  if ((t & 31) == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_acc[t >> 5][e] = a[e];
+  }
+  __syncthreads();
+  if (t < 8) {
+    double tot = 0.0;
+    for (int wdx = 0; wdx < kColThreads / 32; ++wdx) tot += s_acc[wdx][t];
+    s_acc[0][t] = tot;        // each of the 8 threads overwrites only its own column of row 0 after reading it
+  }
+  __syncthreads();
   if (t < 4) {
     const int c = c0 + t;
     const double s1 = s_acc[0][t], s2 = s_acc[0][4 + t];

@@ -15,6 +15,7 @@
 //   warp 4     streams the pre-packed weight block with cp.async.bulk (TMA unit) onto the same mbarrier;
 //   warp 5     one lane issues tcgen05.mma 128 x ncols x 16 and commits.
 // The same kernel runs dense GEMMs (k = 1 convolutions) with an identity gather (pairs == nullptr).
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "bn_common.cuh"
@@ -197,6 +198,219 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Same arithmetic, organised for reuse and overlap: each CTA owns a contiguous run of tiles (so consecutive tiles
+// mostly share their offset k), keeps B_k resident in shared memory until k changes, streams the gathered A blocks
+// through a ring that runs across tile boundaries, and double-buffers the TMEM accumulator so that the gathers and
+// MMAs of tile t+1 proceed under the epilogue of tile t.  Warp roles (320 threads):
+//   0-3  gather producers   cp.async rows -> A ring slot -> full_a[slot]
+//   4    weight loader      cp.async.bulk B_k (all k-blocks) -> b_full, after b_free of the previous offset
+//   5    MMA issuer         tcgen05.mma into accumulator buffer (tile & 1); commits empty_a[slot], acc_full[buf], b_free
+//   6-9  epilogue           tcgen05.ld -> per-warp padded staging -> coalesced 128-byte row segments -> acc_empty[buf]
+constexpr int kV3Threads = 320;
+constexpr int kV3MaxSlots = 8;
+constexpr int kV3StageFloats = 32 * 36;        // one warp: 32 rows x (32 + 4 pad) floats
+
+struct V3Header {
+  uint64_t full_a[kV3MaxSlots];
+  uint64_t empty_a[kV3MaxSlots];
+  uint64_t b_full, b_free;
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  int32_t off[40];
+  int32_t idx[2][kTileRows];
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kV3Threads)
+conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restrict__ pairs,
+                        const int32_t* __restrict__ off, int K, int gather_col, int64_t n_identity, int red, int ncols,
+                        const uint8_t* __restrict__ wpacked, float* __restrict__ P, int nslots, int tcols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nkb = (red + 63) / 64;
+  const int b_bytes = ncols * kBlockRowBytes;
+  uint8_t* b_region = smem;
+  uint8_t* a_ring = smem + (size_t)nkb * b_bytes;
+  float* staging = reinterpret_cast<float*>(a_ring + (size_t)nslots * kBlockBytes);
+  V3Header* hdr = reinterpret_cast<V3Header*>(reinterpret_cast<uint8_t*>(staging) + 4 * kV3StageFloats * sizeof(float));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- schedule: this CTA's run of tiles
+  int T;
+  if (pairs != nullptr) {
+    if (tid <= K) hdr->off[tid] = __ldg(off + tid);
+    __syncthreads();
+    T = 0;
+    for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
+  } else {
+    T = (int)((n_identity + kTileRows - 1) / kTileRows);
+  }
+  const int chunk = (T + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int g0 = (int)blockIdx.x * chunk;
+  const int g1 = g0 + chunk < T ? g0 + chunk : T;
+  if (g0 >= g1) return;                                    // uniform per CTA
+
+  if (tid == 0) {
+    for (int s = 0; s < nslots; ++s) {
+      mbar_init(&hdr->full_a[s], kPProducers);
+      mbar_init(&hdr->empty_a[s], 1);
+    }
+    mbar_init(&hdr->b_full, 1);
+    mbar_init(&hdr->b_free, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&hdr->acc_full[b], 1);
+      mbar_init(&hdr->acc_empty[b], kPProducers);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)(2 * tcols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  auto tile_of = [&](int g, int* k, int* begin, int* end) {
+    if (pairs != nullptr) {
+      pair_tile(hdr->off, K, g, kTileRows, k, begin, end);
+    } else {
+      *k = 0;
+      *begin = g * kTileRows;
+      *end = (int)min((int64_t)*begin + kTileRows, n_identity);
+    }
+  };
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ gather producers
+    uint32_t cnt = 0;
+    for (int g = g0; g < g1; ++g) {
+      int k, begin, end;
+      tile_of(g, &k, &begin, &end);
+      const int p = begin + tid;
+      int gi = -1;
+      if (p < end) {
+        if (pairs != nullptr) {
+          const int2 pr = __ldg(pairs + p);
+          gi = gather_col ? pr.y : pr.x;
+        } else {
+          gi = p;
+        }
+      }
+      const int ib = (g - g0) & 1;
+      hdr->idx[ib][tid] = gi;
+      named_bar_sync(1, kPProducers);
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        const int slot = (int)(cnt % (uint32_t)nslots);
+        const uint32_t use = cnt / (uint32_t)nslots;
+        if (use > 0) mbar_wait(&hdr->empty_a[slot], (use & 1) ^ 1);
+        const int width = red - kb * 64 < 64 ? red - kb * 64 : 64;
+        gather_block_bf16(a_ring + (size_t)slot * kBlockBytes, in, red, kb * 64, width >> 3, tid, hdr->idx[ib]);
+        cp_async_arrive_noinc(&hdr->full_a[slot]);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ weight loader
+    if (lane == 0) {
+      int cur_k = -1;
+      uint32_t nb = 0;
+      for (int g = g0; g < g1; ++g) {
+        int k, begin, end;
+        tile_of(g, &k, &begin, &end);
+        if (k == cur_k) continue;
+        if (nb > 0) mbar_wait(&hdr->b_free, (nb - 1) & 1);     // every MMA that read the previous B_k has completed
+        mbar_arrive_expect_tx(&hdr->b_full, (uint32_t)(nkb * b_bytes));
+        for (int kb = 0; kb < nkb; ++kb)
+          bulk_g2s(b_region + (size_t)kb * b_bytes, wpacked + ((size_t)k * nkb + kb) * b_bytes, (uint32_t)b_bytes,
+                   &hdr->b_full);
+        cur_k = k;
+        ++nb;
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, ncols, 0, 0);
+      int cur_k = -1;
+      uint32_t nb = 0, cnt = 0;
+      int k, begin, end;
+      tile_of(g0, &k, &begin, &end);
+      for (int g = g0; g < g1; ++g) {
+        const int it = g - g0, buf = it & 1;
+        const uint32_t ub = (uint32_t)it >> 1;
+        if (ub > 0) mbar_wait(&hdr->acc_empty[buf], (ub & 1) ^ 1);   // epilogue has drained this accumulator
+        if (k != cur_k) {
+          mbar_wait(&hdr->b_full, nb & 1);
+          ++nb;
+          cur_k = k;
+        }
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * tcols);
+        for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+          const int slot = (int)(cnt % (uint32_t)nslots);
+          const uint32_t use = cnt / (uint32_t)nslots;
+          mbar_wait(&hdr->full_a[slot], use & 1);
+          fence_proxy_async_smem();
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_ring + (size_t)slot * kBlockBytes);
+          const uint32_t b_addr = smem_u32(b_region + (size_t)kb * b_bytes);
+          const int ksteps = (red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4;
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_bf16(tmem_d, smem_desc_sw128(a_addr + kk * 32, 16, 1024), smem_desc_sw128(b_addr + kk * 32, 16, 1024),
+                      idesc, (kb | kk) != 0);
+          umma_commit(&hdr->empty_a[slot]);
+        }
+        umma_commit(&hdr->acc_full[buf]);
+        int nk = k, nbeg, nend;
+        if (g + 1 < g1) {
+          tile_of(g + 1, &nk, &nbeg, &nend);
+          if (nk != k) umma_commit(&hdr->b_free);
+        }
+        k = nk;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (TMEM quadrant = warp % 4)
+    const int q = warp & 3;
+    float* st = staging + (size_t)(warp - 6) * kV3StageFloats;
+    for (int g = g0; g < g1; ++g) {
+      int k, begin, end;
+      tile_of(g, &k, &begin, &end);
+      const int it = g - g0, buf = it & 1;
+      mbar_wait(&hdr->acc_full[buf], ((uint32_t)it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * tcols) + ((uint32_t)(q * 32) << 16);
+      const int row0 = begin + q * 32;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(st + lane * 36 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {                   // a warp store = 4 rows x 128 contiguous bytes
+          const int r = i8 * 4 + (lane >> 3);
+          const int p = row0 + r;
+          if (p < end)
+            *reinterpret_cast<float4*>(P + (int64_t)p * ncols + c0 + (lane & 7) * 4) =
+                *reinterpret_cast<const float4*>(st + r * 36 + (lane & 7) * 4);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(&hdr->acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)(2 * tcols));
 }
 
 // ------------------------------------------------------------------------------------------------ sorted scatter
@@ -459,6 +673,43 @@ int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t*
   FT3D_REQUIRE(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)partial_out & 15) == 0 && ((uintptr_t)wpacked & 15) == 0,
                "ft3d_conv_pairs_tc: pointers must be 16-byte aligned");
   const int nkb = (red + 63) / 64;
+  // ---- persistent weight-stationary variant whenever B_k and >= 2 ring slots fit (everything but 384-wide operands)
+  {
+    const int b_total = nkb * ncols * tc::kBlockRowBytes;
+    const int fixed = b_total + 4 * kV3StageFloats * (int)sizeof(float) + (int)sizeof(V3Header) + 1024;
+    int nslots = (226 * 1024 - fixed) / tc::kBlockBytes;
+    static int use_v3 = -1;
+    if (use_v3 < 0) {
+      const char* e = getenv("FT3D_PAIRS_PERSISTENT");
+      use_v3 = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    if (use_v3 && ncols <= 256 && nslots >= 2) {
+      const int want = 2 * nkb < 3 ? 3 : 2 * nkb;            // two tiles of A blocks in flight
+      if (nslots > want) nslots = want;
+      if (nslots > kV3MaxSlots) nslots = kV3MaxSlots;
+      // prefer two resident CTAs when that costs no ring depth below one full tile
+      if (fixed + nslots * tc::kBlockBytes > 113 * 1024 && fixed + nkb * tc::kBlockBytes <= 113 * 1024 && nkb >= 2)
+        nslots = (113 * 1024 - fixed) / tc::kBlockBytes;
+      const int smem_bytes = fixed + nslots * tc::kBlockBytes;
+      int ctas_per_sm = (227 * 1024) / smem_bytes;                 // shared memory
+      const int by_tmem = 512 / (2 * tmem_cols_pow2(ncols));        // two accumulator buffers per CTA
+      if (ctas_per_sm > by_tmem) ctas_per_sm = by_tmem;
+      if (ctas_per_sm > 4) ctas_per_sm = 4;
+      if (ctas_per_sm < 1) ctas_per_sm = 1;
+      static int configured3 = 0;
+      if (!configured3) {
+        FT3D_CUDA(cudaFuncSetAttribute(conv_pairs_tc_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured3 = 1;
+      }
+      const int64_t tiles = (max_pairs + tc::kTileRows - 1) / tc::kTileRows + (pairs ? K : 0);
+      const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+      const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+      conv_pairs_tc_v3_kernel<<<grid, kV3Threads, smem_bytes, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)in_bf16, (const int2*)pairs, pair_offsets, K, gather_col, max_pairs, red, ncols,
+          (const uint8_t*)wpacked, partial_out, nslots, tmem_cols_pow2(ncols));
+      return check_launch("ft3d_conv_pairs_tc");
+    }
+  }
   const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes;
   const int tail = (int)sizeof(PairsSmemHeader) + 1024 + 128;
   int nstages = (226 * 1024 - tail) / stage_bytes;

@@ -67,6 +67,53 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int K, int cin,
   }
 }
 
+// All weight images of a model in ONE launch (they are re-packed after every optimizer step): `desc` lists, per
+// image, the fp32 source, the destination and the first 16-byte chunk it owns in the launch's flat chunk index.
+struct PackDesc {
+  const float* w;
+  uint4* img;
+  int32_t K, cin, cout, w_transposed;
+  int64_t chunk_begin;
+};
+
+__global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ desc, int n_desc, int64_t total) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_desc - 1;             // last descriptor with chunk_begin <= t
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&desc[mid].chunk_begin) <= t) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc d = desc[lo];
+    const int64_t u = t - d.chunk_begin;
+    const int red = d.w_transposed ? d.cout : d.cin;
+    const int ncols = d.w_transposed ? d.cin : d.cout;
+    const int nkb = (red + 63) / 64;
+    const int pc = (int)(u & 7);
+    const int64_t rowid = u >> 3;
+    const int n = (int)(rowid % ncols);
+    const int64_t blk = rowid / ncols;
+    const int kb = (int)(blk % nkb);
+    const int k = (int)(blk / nkb);
+    const int c = pc ^ (n & 7);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int r = kb * 64 + c * 8 + e;
+      float x = 0.f;
+      if (r < red)
+        x = d.w_transposed ? __ldg(d.w + ((int64_t)k * d.cin + n) * d.cout + r)
+                           : __ldg(d.w + ((int64_t)k * d.cin + r) * d.cout + n);
+      v[e] = x;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    d.img[u] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward / dgrad
 struct ConvSmemHeader {
   uint64_t full[kMaxStages];
@@ -382,6 +429,16 @@ int ft3d_conv_pack_weights(const float* w, int32_t K, int32_t cin, int32_t cout,
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, K, cin, cout, w_transposed,
                                                                               (uint4*)wpacked);
   return check_launch("ft3d_conv_pack_weights");
+}
+
+size_t ft3d_conv_pack_desc_bytes(void) { return sizeof(PackDesc); }
+
+int ft3d_conv_pack_weights_multi(const void* desc, int32_t n_desc, int64_t total_chunks, ft3d_stream_t stream) {
+  if (n_desc == 0 || total_chunks == 0) return FT3D_OK;
+  FT3D_REQUIRE(desc && n_desc > 0 && total_chunks > 0, "ft3d_conv_pack_weights_multi: bad arguments");
+  pack_weights_multi_kernel<<<grid_for(total_chunks, 256), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)desc, n_desc,
+                                                                                           total_chunks);
+  return check_launch("ft3d_conv_pack_weights_multi");
 }
 
 int ft3d_conv_gather_tc(const float* in, const int32_t* nbr, int64_t n_out, int32_t K, int32_t kpad,

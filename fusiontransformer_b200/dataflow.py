@@ -71,12 +71,11 @@ def prepare_batch(batch, device="cuda"):
     """Everything of a training step that depends only on the batch's points: upload (if ``batch`` is a HostBatch),
     device-side voxelization + dedup (a1-a3), and the GeometryPlan of the forward pass (plan.py).  Meant to run one
     step ahead on ``plan.Prefetcher``'s side stream.  Returns the plan; ``plan.extras`` carries
-    ``lidar`` (SparseTensor with ``.plan`` attached), ``rc``, ``bidx``, ``labels``, ``inverse``, ``kept``."""
+    ``lidar`` (SparseTensor; pass ``plan=`` to the model -- no back-reference, so no reference cycle), ``rc``, ``bidx``, ``labels``, ``inverse``, ``kept``."""
     from .plan import build_plan
     db = to_device(batch, device) if isinstance(batch, HostBatch) else batch
     lidar, rc, bidx, labels, inv, kept = voxelize_batch(db)
     plan = build_plan(lidar.C)
-    lidar.plan = plan
     plan.extras.update(lidar=lidar, rc=rc, bidx=bidx, labels=labels, inverse=inv, kept=kept, batch=db.points,
                        batch_feats=db.feats, batch_sid=db.scan_id, batch_img=db.img_idx, batch_labels=db.labels)
     return plan

@@ -27,7 +27,7 @@ from . import nn as spnn
 from .functional import conv_geometry
 from .sparse_tensor import SparseTensor
 
-__all__ = ["conv_bn_act", "fuse", "unfuse", "join_side_streams"]
+__all__ = ["conv_bn_act", "fuse", "unfuse", "join_side_streams", "weight_packer"]
 
 
 class _SideStream:
@@ -299,6 +299,14 @@ def _residual_forward(self, x):
     h = conv_bn_act(x, nm[0], nm[1], True)
     shortcut = x.F if not dm else conv_bn_act(x, dm[0], dm[1], False).F
     return conv_bn_act(h, nm[3], nm[4], True, res=shortcut.contiguous())
+
+
+def weight_packer(model: nn.Module):
+    """ops.WeightPacker over every tensor-core conv kernel of ``model``: call ``.pack()`` once per step (after the
+    optimizer update) instead of one pack launch per layer and orientation."""
+    ks = [m.kernel for m in model.modules() if isinstance(m, spnn.Conv3d)
+          and conv_engine.pairs_ok(m.kernel.shape[-2], m.kernel.shape[-1])]
+    return ops.WeightPacker(ks)
 
 
 def fuse(model: nn.Module) -> nn.Module:

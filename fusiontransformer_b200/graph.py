@@ -41,11 +41,16 @@ class _Slot:
         self.buf = torch.full((cap_rows,) + tuple(tail_shape), pad, dtype=dtype, device=device)
         self.pad, self.used = pad, 0
 
-    def load(self, src: torch.Tensor):
+    def load(self, src: torch.Tensor, copies, fills):
+        """Queue ``buf[:n] <- src`` (and the re-padding of rows a larger previous batch left behind) on the batched
+        copy / fill lists; StaticGeometry.load issues them as a handful of multi-tensor launches."""
         n = src.shape[0]
-        self.buf[:n].copy_(src.to(self.buf.dtype) if src.dtype != self.buf.dtype else src, non_blocking=True)
+        copies.setdefault(self.buf.dtype, ([], []))
+        dst, srcs = copies[self.buf.dtype]
+        dst.append(self.buf[:n])
+        srcs.append(src.to(self.buf.dtype) if src.dtype != self.buf.dtype else src)
         if n < self.used:
-            self.buf[n:self.used].fill_(self.pad)
+            fills.setdefault((self.buf.dtype, self.pad), []).append(self.buf[n:self.used])
         self.used = n
 
 
@@ -138,32 +143,39 @@ class StaticGeometry:
     def load(self, plan: GeometryPlan):
         """Copy one batch's geometry and inputs into the static buffers (enqueued on the current stream)."""
         ex, S = plan.extras, self.slots
-        S["point_coords"].load(plan.point_coords)
-        S["idx_query"].load(plan.idx_query)
-        S["counts"].load(plan.counts)
-        S["feats"].load(ex["lidar"].F)
-        S["coords_in"].load(ex["lidar"].C)
-        S["rc"].load(ex["rc"])
-        S["bidx"].load(ex["bidx"])
-        S["labels"].load(ex["labels"])
+        copies, fills = {}, {}
+        S["point_coords"].load(plan.point_coords, copies, fills)
+        S["idx_query"].load(plan.idx_query, copies, fills)
+        S["counts"].load(plan.counts, copies, fills)
+        S["feats"].load(ex["lidar"].F, copies, fills)
+        S["coords_in"].load(ex["lidar"].C, copies, fills)
+        S["rc"].load(ex["rc"], copies, fills)
+        S["bidx"].load(ex["bidx"], copies, fills)
+        S["labels"].load(ex["labels"], copies, fills)
         for s in self.strides:
-            S["C%d" % s].load(plan.coord_maps[s])
+            S["C%d" % s].load(plan.coord_maps[s], copies, fills)
         for key, km in plan.kernel_maps.items():
             L = km.num_pairs()
             if key + ".nbr" in S:
-                S[key + ".nbr"].load(km.nbr)
+                S[key + ".nbr"].load(km.nbr, copies, fills)
             if key + ".nbrT" in S:
-                S[key + ".nbrT"].load(km.nbrT)
-            S[key + ".pairs"].load(km.pairs_padded[:L])
-            S[key + ".offsets"].load(km.pair_offsets)
-            S[key + ".ppos"].load(km.ppos)
-            S[key + ".pposT"].load(km.pposT)
+                S[key + ".nbrT"].load(km.nbrT, copies, fills)
+            S[key + ".pairs"].load(km.pairs_padded[:L], copies, fills)
+            S[key + ".offsets"].load(km.pair_offsets, copies, fills)
+            S[key + ".ppos"].load(km.ppos, copies, fills)
+            S[key + ".pposT"].load(km.pposT, copies, fills)
         for s, (idx, cnt) in plan.p2v.items():
-            S["p2v%d.idx" % s].load(idx)
-            S["p2v%d.cnt" % s].load(cnt)
+            S["p2v%d.idx" % s].load(idx, copies, fills)
+            S["p2v%d.cnt" % s].load(cnt, copies, fills)
         for s, (idx, w) in plan.v2p.items():
-            S["v2p%d.idx" % s].load(idx)
-            S["v2p%d.w" % s].load(w)
+            S["v2p%d.idx" % s].load(idx, copies, fills)
+            S["v2p%d.w" % s].load(w, copies, fills)
+        for dst, srcs in copies.values():
+            torch._foreach_copy_(dst, srcs, non_blocking=True)
+        for (dtype, pad), views in fills.items():
+            torch._foreach_zero_(views)
+            if pad != 0:
+                torch._foreach_add_(views, pad)
         row = self._counts_host[self._ring]
         self._ring = (self._ring + 1) % self._counts_host.shape[0]
         row[0] = plan.point_coords.shape[0]
@@ -176,8 +188,8 @@ class StaticGeometry:
         p = GeometryPlan(point_coords=self.point_coords, sparse_hash=None, idx_query=self.idx_query, counts=self.counts)
         p.coord_maps, p.kernel_maps, p.tables = dict(self.coord_maps), dict(self.kernel_maps), {}
         p.p2v, p.v2p = dict(self.p2v), dict(self.v2p)
-        lidar = SparseTensor(self.feats, self.coords_in)
-        lidar.plan = p
+        lidar = SparseTensor(self.feats, self.coords_in)      # no back-reference to p: a cycle would park every
+                                                                # batch's tensors until the cyclic GC runs
         p.extras.update(lidar=lidar, rc=self.rc, bidx=self.bidx, labels=self.labels)
         return p
 
@@ -227,6 +239,7 @@ class GraphedStep:
             calls0 = _lib.launch_count(_lib.lib().calls)
             g = torch.cuda.CUDAGraph()
             ops.FORCE_REPACK = True                         # weight images must be re-packed inside every replay
+            ops.PACK_EPOCH += 1
             try:
                 with torch.cuda.graph(g, stream=self.stream):
                     self.loss = self.body(splan)

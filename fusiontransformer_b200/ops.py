@@ -328,6 +328,45 @@ def conv_wgrad_f32(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
 
 _PACK_CACHE = {}
 FORCE_REPACK = False     # graph.py sets this while capturing: the pack launch must be part of every replay
+PACK_EPOCH = 0           # bumped per capture; images packed by pack_all() inside the capture are not packed twice
+
+
+class WeightPacker:
+    """All bf16 weight images of a set of conv kernels (both orientations) in ONE launch per step.
+
+    Built once (the fp32 parameters and the images keep their addresses); ``pack()`` refreshes every image and marks
+    the per-tensor cache entries fresh, so the per-layer ``packed_weights`` calls of that step are cache hits."""
+
+    def __init__(self, kernels):
+        import struct
+        import weakref
+        self.entries = []
+        recs, chunk = [], 0
+        for p in kernels:
+            w = p.detach()
+            w3 = w.unsqueeze(0) if w.dim() == 2 else w
+            k, cin, cout = w3.shape
+            for wt in (False, True):
+                red, ncols = (cout, cin) if wt else (cin, cout)
+                nbytes = int(lib().conv_packed_bytes(k, red, ncols))
+                img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+                recs.append(struct.pack("<QQiiiiq", w3.data_ptr(), img.data_ptr(), k, cin, cout, int(wt), chunk))
+                chunk += nbytes // 16
+                self.entries.append((weakref.ref(p), wt, w3.data_ptr(), img))
+        assert lib().conv_pack_desc_bytes() == 40
+        self.total = chunk
+        self.n = len(recs)
+        dev = kernels[0].device if kernels else None
+        self.desc = (torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev) if recs else None)
+
+    def pack(self):
+        if not self.n:
+            return
+        lib().conv_pack_weights_multi(self.desc.data_ptr(), self.n, self.total, _stream())
+        for ref, wt, ptr, img in self.entries:
+            p = ref()
+            if p is not None:
+                _PACK_CACHE[(id(p), wt)] = (ref, p._version, ptr, img, PACK_EPOCH)
 
 
 def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Tensor:
@@ -339,8 +378,8 @@ def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Ten
     owner = w if owner is None else owner
     key = (id(owner), bool(w_transposed))
     hit = _PACK_CACHE.get(key)
-    if (not FORCE_REPACK and hit is not None and hit[0]() is owner and hit[1] == owner._version
-            and hit[2] == w.data_ptr()):
+    if (hit is not None and hit[0]() is owner and hit[1] == owner._version and hit[2] == w.data_ptr()
+            and (not FORCE_REPACK or (len(hit) > 4 and hit[4] == PACK_EPOCH))):
         return hit[3]
     k, cin, cout = w.shape
     red, ncols = (cout, cin) if w_transposed else (cin, cout)
@@ -351,7 +390,7 @@ def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Ten
     if len(_PACK_CACHE) > 512:
         for kk in [kk for kk, v in _PACK_CACHE.items() if v[0]() is None]:
             del _PACK_CACHE[kk]
-    _PACK_CACHE[key] = (weakref.ref(owner), owner._version, w.data_ptr(), img)
+    _PACK_CACHE[key] = (weakref.ref(owner), owner._version, w.data_ptr(), img, -1)
     return img
 
 

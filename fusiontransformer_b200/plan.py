@@ -109,11 +109,11 @@ class Prefetcher:
     ``submit`` queues the work for the NEXT step; ``get`` waits for the worker, makes the consumer's stream wait for
     the side stream and tells the caching allocator which stream now uses the tensors."""
 
-    def __init__(self, device=None, threaded: bool = True):
+    def __init__(self, device=None, threaded: bool = False, priority: int = -1):
         import queue
         import threading
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.stream = torch.cuda.Stream(device=self.device, priority=priority)
         self._pending = None
         self._threaded = threaded
         if threaded:

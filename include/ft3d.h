@@ -158,6 +158,11 @@ int ft3d_conv_gather_f32(const float* in, const int32_t* nbr, int64_t n_out, int
 size_t ft3d_conv_packed_bytes(int32_t K, int32_t red, int32_t ncols);
 int ft3d_conv_pack_weights(const float* w, int32_t K, int32_t cin, int32_t cout,
                            int32_t w_transposed, void* wpacked, ft3d_stream_t stream);
+/* Every weight image of a model in one launch (they are re-packed after each optimizer step).  desc: device array of
+ * n_desc records { const float* w; void* img; int32 K, cin, cout, w_transposed; int64 chunk_begin; } (40 bytes,
+ * ft3d_conv_pack_desc_bytes()), chunk_begin = running sum of ft3d_conv_packed_bytes(...)/16 of the records before. */
+size_t ft3d_conv_pack_desc_bytes(void);
+int ft3d_conv_pack_weights_multi(const void* desc, int32_t n_desc, int64_t total_chunks, ft3d_stream_t stream);
 int ft3d_conv_gather_tc(const float* in, const int32_t* nbr, int64_t n_out, int32_t K,
                         int32_t kpad, int32_t kflip, int32_t red, int32_t ncols,
                         const void* wpacked, float* out, ft3d_stream_t stream);

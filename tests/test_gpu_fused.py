@@ -227,3 +227,23 @@ def test_gradient_arena_sink_equals_autograd_accumulation(monkeypatch, voxels):
     for (name, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert sync.owns(pa), name
         assert (pa.grad - pb.grad).norm().item() <= 1e-3 * pb.grad.norm().item() + 1e-7, name
+
+
+def test_multi_pack_equals_per_layer_pack(monkeypatch):
+    """ops.WeightPacker (all images, one launch) writes the same bytes as ft3d_conv_pack_weights per image."""
+    from fusiontransformer_b200 import ops
+    from fusiontransformer_b200 import spvcnn as sp
+    from fusiontransformer_b200.fused import weight_packer
+    monkeypatch.setenv("FT3D_CONV", "tc")
+    torch.manual_seed(2)
+    net = torch.nn.Sequential(sp.BasicConvolutionBlock(32, 64, ks=2, stride=2), sp.ResidualBlock(64, 128),
+                              sp.ResidualBlock(128, 96)).cuda()
+    packer = weight_packer(net)
+    assert packer.n == 2 * sum(1 for m in net.modules() if hasattr(m, "kernel"))
+    packer.pack()
+    for ref, wt, _, img in packer.entries:
+        p = ref()
+        w = p.detach().unsqueeze(0) if p.dim() == 2 else p.detach()
+        ops._PACK_CACHE.clear()
+        single = ops.packed_weights(w.contiguous(), wt)
+        assert torch.equal(single, img), (tuple(p.shape), wt)

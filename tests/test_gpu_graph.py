@@ -36,7 +36,7 @@ def _trainer(mode, optimize=True):
         ex = plan.extras
         rc = torch.stack([ex["rc"][:, 0] % 90, ex["rc"][:, 1] % 160], 1).contiguous()
         img = ft.nn.functional.lift(fmap, rc, ex["bidx"])
-        out = net(ex["lidar"], img.detach())
+        out = net(ex["lidar"], img.detach(), plan=plan)
         loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], ex["labels"])
         sync.zero_grad()
         loss.backward()

@@ -14,7 +14,7 @@ plan = dataflow.prepare_batch(hb, "cuda")
 n = plan.point_coords.shape[0]
 img = torch.randn(n, 96, device="cuda", generator=g)
 taps_e = {}
-out_e = net(plan.extras["lidar"], img, taps=taps_e)["lidar_seg_logit"]
+out_e = net(plan.extras["lidar"], img, taps=taps_e, plan=plan)["lidar_seg_logit"]
 st = StaticGeometry(plan)
 st.load(plan)
 ops.ROW_COUNTS = st.row_counts
@@ -24,7 +24,7 @@ img_p = torch.zeros(P, 96, device="cuda")
 img_p[:n] = img
 img_p[n:] = 3.0          # garbage in the padding rows of an input
 taps_p = {}
-out_p = net(sp.extras["lidar"], img_p, taps=taps_p)["lidar_seg_logit"]
+out_p = net(sp.extras["lidar"], img_p, taps=taps_p, plan=sp)["lidar_seg_logit"]
 for k in taps_e:
     a, b = taps_e[k], taps_p[k]
     fa, fb = a.F, b.F
