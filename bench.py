@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--reuse-plans", action="store_true", help="diagnostic only: time the compute with cached geometry")
     ap.add_argument("--trace", type=int, default=0, metavar="N",
                     help="after the timed runs, profile N more steps with torch.profiler and print the GPU kernel table")
+    ap.add_argument("--trace-top", type=int, default=60)
+    ap.add_argument("--trace-dump", default="", help="CSV of the last traced step, one row per GPU launch")
     ap.add_argument("--diag", action="store_true", help="print host-side enqueue time per phase (stderr)")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="build each batch's geometry inside its own step (host reads stall the launch queue)")
@@ -196,7 +198,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a mismatched collective must fail in minutes, not hold the box for NCCL's 10-minute default
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
     wl = WORKLOADS[args.workload]
@@ -223,7 +227,7 @@ def main():
     # built on a high-priority side stream while batch i's convolutions run (fusiontransformer_b200/plan.py).
     from fusiontransformer_b200.plan import Prefetcher
     pre = Prefetcher(dev, threaded=not args.no_prefetch_thread,
-                     priority=int(os.environ.get("FT3D_PREFETCH_PRIORITY", "-1"))) if args.prefetch else None
+                     priority=int(os.environ.get("FT3D_PREFETCH_PRIORITY", "-2"))) if args.prefetch else None
 
     diag = {} if args.diag else None
 
@@ -414,33 +418,77 @@ def main():
                         "algorithmic_mb_per_launch": by / len(convs) / 1e6,
                         "algorithmic_gflop_per_launch": fl / len(convs) / 1e9,
                         "tflops": fl / t_s / 1e12, "gbs": by / t_s / 1e9,
-                        "share_of_step": tot[dom][0] / nprof / step_ms,
+                        "share_of_step": tot[dom][0] / nprof / (ms / args.steps),
+                        "share_of_kernel_time": tot[dom][0] / max(sum(v[0] for v in tot.values()), 1e-9),
                         "note": "time = CUDA events around every conv_pairs_tc launch on the launching stream, "
-                                "summed over %d separately profiled steps launched kernel by kernel" % nprof}
+                                "summed over %d separately profiled steps launched kernel by kernel; share_of_step = that time per "
+                                "step / the graph-replayed ms_per_step (kernels of other streams overlap it); "
+                                "share_of_kernel_time = / the sum over all libft3d entry points" % nprof}
 
     if args.trace and world == 1:
-        from torch.autograd import DeviceType
+        # torch.profiler (CUPTI) timeline of N more steps: per-kernel table, per-stream busy time, idle gaps
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for i in range(args.trace):
                 train_step(resident[i % nbatches], resident[(i + 1) % nbatches])
             torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) / args.trace * 1e3
-        agg, t_lo, t_hi = {}, None, None
-        for e in prof.events():
-            if e.device_type == DeviceType.CUDA:
-                a = agg.setdefault(e.name, [0.0, 0])
-                a[0] += e.device_time_total
-                a[1] += 1
-        rows = sorted(((v[0] / args.trace / 1e3, v[1] / args.trace, k) for k, v in agg.items()), reverse=True)
-        print("trace: wall %.2f ms/step under profiler, sum of GPU kernel time %.2f ms/step, %d launches/step"
-              % (wall, sum(r[0] for r in rows), sum(r[1] for r in rows)), file=sys.stderr)
-        for ms_, cnt, key in rows[:40]:
-            print("  %8.3f ms %6.1f x  %s" % (ms_, cnt, key[:120]), file=sys.stderr)
         if pre is not None and pre._pending is not None:
             pre.get()
+        tf = tempfile.NamedTemporaryFile(suffix=".json", delete=False).name
+        prof.export_chrome_trace(tf)
+        evs = [e for e in json.load(open(tf))["traceEvents"]
+               if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
+        os.unlink(tf)
+        agg, streams = {}, {}
+        for e in evs:
+            a = agg.setdefault(e["name"], [0.0, 0])
+            a[0] += e["dur"]
+            a[1] += 1
+            streams.setdefault(e["args"].get("stream"), []).append((e["ts"], e["ts"] + e["dur"], e["name"]))
+        rows = sorted(((v[0] / args.trace / 1e3, v[1] / args.trace, k) for k, v in agg.items()), reverse=True)
+        iv = sorted((a, b) for v in streams.values() for a, b, _ in v)
+        busy, cur_a, cur_b = 0.0, None, None
+        for a, b in iv:
+            if cur_b is None or a > cur_b:
+                if cur_b is not None:
+                    busy += cur_b - cur_a
+                cur_a, cur_b = a, b
+            else:
+                cur_b = max(cur_b, b)
+        if cur_b is not None:
+            busy += cur_b - cur_a
+        span = (iv[-1][1] - iv[0][0]) if iv else 0.0
+        print("trace: wall %.2f ms/step under profiler, GPU span %.2f ms/step, any-stream busy %.2f ms/step, "
+              "sum of kernel time %.2f ms/step, %d launches/step"
+              % (wall, span / args.trace / 1e3, busy / args.trace / 1e3, sum(r[0] for r in rows), sum(r[1] for r in rows)),
+              file=sys.stderr)
+        for sid, v in sorted(streams.items(), key=lambda kv: -sum(b - a for a, b, _ in kv[1])):
+            v.sort()
+            tot = sum(b - a for a, b, _ in v)
+            gaps = sorted(((v[i + 1][0] - v[i][1], v[i][2][:50], v[i + 1][2][:50]) for i in range(len(v) - 1)), reverse=True)
+            small = sum(g for g, _, _ in gaps if 0 < g < 50.0)
+            print("  stream %s: %d launches/step, busy %.2f ms/step, gaps<50us sum %.2f ms/step" %
+                  (sid, len(v) / args.trace, tot / args.trace / 1e3, small / args.trace / 1e3), file=sys.stderr)
+            for g, n0, n1 in gaps[:6]:
+                print("      gap %8.1f us after %s before %s" % (g, n0, n1), file=sys.stderr)
+        if args.trace_dump:
+            # the last traced step, launch by launch (all streams): analysed offline (tools/analyze_trace.py)
+            cut = iv[0][0] + span * (args.trace - 1) / args.trace
+            with open(args.trace_dump, "w") as f:
+                f.write("ts_us,dur_us,stream,grid,block,smem,regs,name\n")
+                for e in sorted(evs, key=lambda e: e["ts"]):
+                    if e["ts"] < cut:
+                        continue
+                    a_ = e["args"]
+                    f.write("%.3f,%.3f,%s,%s,%s,%s,%s,\"%s\"\n" % (
+                        e["ts"] - cut, e["dur"], a_.get("stream"), "x".join(map(str, a_.get("grid", []))),
+                        "x".join(map(str, a_.get("block", []))), a_.get("shared memory", ""),
+                        a_.get("registers per thread", ""), e["name"][:90].replace('"', "'")))
+        for ms_, cnt, key in rows[:args.trace_top]:
+            print("  %8.3f ms %6.1f x %7.1f us  %s" % (ms_, cnt, 1e3 * ms_ / max(cnt, 1e-9), key[:110]), file=sys.stderr)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -624,6 +624,200 @@ conv_wgrad_pairs_tc_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ persistent wgrad
+// Same arithmetic as conv_wgrad_pairs_tc_kernel, organised like the persistent forward kernel: a CTA owns a contiguous
+// run of units (unit = one 128-pair tile x one 128-wide Cin block, Cin-block-major so that consecutive units share
+// their (offset, Cin block) accumulator), streams the gathered A/G stages through a ring that runs across unit
+// boundaries, keeps the running sum in one of TWO TMEM accumulators and flushes it (red.global.add.v4.f32 through a
+// per-warp staging transpose => full 128-byte segments) only when the (offset, Cin block) changes, while the gathers
+// and MMAs of the next group proceed.  Warp roles (320 threads):
+//   0-3  gather producers   4  idle   5  MMA issuer   6-9  flush (TMEM quadrant = warp % 4)
+constexpr int kWg2MaxSlots = 6;
+
+struct Wg2Header {
+  uint64_t full[kWg2MaxSlots];
+  uint64_t empty[kWg2MaxSlots];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  int32_t off[40];
+  int32_t pa[2][kTileRows];
+  int32_t pb[2][kTileRows];
+};
+
+__global__ void __launch_bounds__(kV3Threads)
+conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                              const int2* __restrict__ pairs, const int32_t* __restrict__ off, int K, int ca,
+                              int64_t n_identity, int cin, int cout, float* __restrict__ gw, int nslots, int tcols,
+                              int a_blocks) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nb_blocks = (cout + 63) / 64;
+  const int stage_bytes = (a_blocks + nb_blocks) * kBlockBytes;
+  float* staging = reinterpret_cast<float*>(smem + (size_t)nslots * stage_bytes);
+  Wg2Header* hdr = reinterpret_cast<Wg2Header*>(reinterpret_cast<uint8_t*>(staging) + 4 * kV3StageFloats * sizeof(float));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  int T;
+  if (pairs != nullptr) {
+    if (tid <= K) hdr->off[tid] = __ldg(off + tid);
+    __syncthreads();
+    T = 0;
+    for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
+  } else {
+    T = (int)((n_identity + kTileRows - 1) / kTileRows);
+  }
+  const int MB = (cin + 127) / 128;
+  const int U = T * MB;
+  const int chunk = (U + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int u0 = (int)blockIdx.x * chunk;
+  const int u1 = u0 + chunk < U ? u0 + chunk : U;
+  if (u0 >= u1) return;                                    // uniform per CTA
+
+  if (tid == 0) {
+    for (int s = 0; s < nslots; ++s) {
+      mbar_init(&hdr->full[s], kPProducers);
+      mbar_init(&hdr->empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hdr->acc_full[i], 1);
+      mbar_init(&hdr->acc_empty[i], kPProducers);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)(2 * tcols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  auto unit_of = [&](int u, int* mb, int* k, int* begin, int* end) {
+    *mb = u / T;
+    const int t = u - *mb * T;
+    if (pairs != nullptr) {
+      pair_tile(hdr->off, K, t, kTileRows, k, begin, end);
+    } else {
+      *k = 0;
+      *begin = t * kTileRows;
+      *end = (int)min((int64_t)*begin + kTileRows, n_identity);
+    }
+  };
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ gather producers
+    for (int u = u0; u < u1; ++u) {
+      int mb, k, begin, end;
+      unit_of(u, &mb, &k, &begin, &end);
+      const int p = begin + tid;
+      int ia = -1, ib = -1;
+      if (p < end) {
+        if (pairs != nullptr) {
+          const int2 pr = __ldg(pairs + p);
+          ia = ca ? pr.y : pr.x;
+          ib = ca ? pr.x : pr.y;
+        } else {
+          ia = ib = p;
+        }
+      }
+      const int it = u - u0, dbuf = it & 1;
+      hdr->pa[dbuf][tid] = ia;
+      hdr->pb[dbuf][tid] = ib;
+      named_bar_sync(1, kPProducers);
+      const int slot = it % nslots;
+      const uint32_t use = (uint32_t)(it / nslots);
+      if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
+      uint8_t* st = smem + (size_t)slot * stage_bytes;
+      const int m_valid = cin - mb * 128 < 128 ? cin - mb * 128 : 128;
+      for (int blk = 0; blk * 64 < m_valid; ++blk) {
+        const int width = m_valid - blk * 64 < 64 ? m_valid - blk * 64 : 64;
+        gather_block_bf16(st + blk * kBlockBytes, a, cin, mb * 128 + blk * 64, width >> 3, tid, hdr->pa[dbuf]);
+      }
+      for (int blk = 0; blk < nb_blocks; ++blk) {
+        const int width = cout - blk * 64 < 64 ? cout - blk * 64 : 64;
+        gather_block_bf16(st + (a_blocks + blk) * kBlockBytes, b, cout, blk * 64, width >> 3, tid, hdr->pb[dbuf]);
+      }
+      cp_async_arrive_noinc(&hdr->full[slot]);
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, cout, 1, 1);
+      int group = -1, pk = -1, pmb = -1;
+      for (int u = u0; u < u1; ++u) {
+        int mb, k, begin, end;
+        unit_of(u, &mb, &k, &begin, &end);
+        const bool fresh = (k != pk || mb != pmb);
+        if (fresh) {
+          if (group >= 0) umma_commit(&hdr->acc_full[group & 1]);     // previous group complete -> flush warps
+          ++group;
+          const uint32_t ub = (uint32_t)group >> 1;
+          if (ub > 0) mbar_wait(&hdr->acc_empty[group & 1], (ub & 1) ^ 1);
+          pk = k;
+          pmb = mb;
+        }
+        const int it = u - u0;
+        const int slot = it % nslots;
+        mbar_wait(&hdr->full[slot], (uint32_t)(it / nslots) & 1);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)((group & 1) * tcols);
+        const uint32_t a_addr = smem_u32(smem + (size_t)slot * stage_bytes);
+        const uint32_t b_addr = a_addr + a_blocks * kBlockBytes;
+        for (int kk = 0; kk < kTileRows / 16; ++kk) {
+          const uint64_t da = smem_desc_sw128(a_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
+          const uint64_t db = smem_desc_sw128(b_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
+          umma_bf16(tmem_d, da, db, idesc, (!fresh || kk != 0) ? 1u : 0u);
+        }
+        umma_commit(&hdr->empty[slot]);
+      }
+      umma_commit(&hdr->acc_full[group & 1]);
+    }
+  } else if (warp >= 6) {
+    // ------------------------------------------------------------------ flush
+    const int q = warp & 3;
+    float* st = staging + (size_t)(warp - 6) * kV3StageFloats;
+    int group = -1, pk = -1, pmb = -1;
+    for (int u = u0; u <= u1; ++u) {
+      int mb = -1, k = -1, begin, end;
+      if (u < u1) unit_of(u, &mb, &k, &begin, &end);
+      if (k == pk && mb == pmb) continue;
+      if (group >= 0) {                                    // group (pk, pmb) is complete
+        const int buf = group & 1;
+        mbar_wait(&hdr->acc_full[buf], ((uint32_t)group >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(buf * tcols) + ((uint32_t)(q * 32) << 16);
+        const int row0 = pmb * 128 + q * 32;
+        for (int c0 = 0; c0 < cout; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(st + lane * 36 + j) = make_float4(
+                __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = i8 * 4 + (lane >> 3);
+            const int row = row0 + r;
+            if (row < cin)
+              atomicAdd(reinterpret_cast<float4*>(gw + ((int64_t)pk * cin + row) * cout + c0 + (lane & 7) * 4),
+                        *reinterpret_cast<const float4*>(st + r * 36 + (lane & 7) * 4));
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(&hdr->acc_empty[buf]);
+      }
+      ++group;
+      pk = k;
+      pmb = mb;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)(2 * tcols));
+}
+
 static int tmem_cols_pow2(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -781,6 +975,42 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
   FT3D_REQUIRE(((uintptr_t)a_bf16 & 15) == 0 && ((uintptr_t)b_bf16 & 15) == 0 && ((uintptr_t)gw & 15) == 0,
                "ft3d_conv_wgrad_pairs_tc: pointers must be 16-byte aligned");
   const int nb_blocks = (cout + 63) / 64;
+  {
+    static int use_v2 = -1;
+    if (use_v2 < 0) {
+      const char* e = getenv("FT3D_WGRAD_PERSISTENT");
+      use_v2 = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    if (use_v2) {
+      const int a_blocks = cin <= 64 ? 1 : 2;
+      const int stage = (a_blocks + nb_blocks) * tc::kBlockBytes;
+      const int fixed = 4 * kV3StageFloats * (int)sizeof(float) + (int)sizeof(Wg2Header) + 1024;
+      const int tcols = tmem_cols_pow2(cout);
+      // two resident CTAs (3-deep rings) when shared memory and TMEM (2 accumulators each) allow, else one CTA
+      int ctas_per_sm = 1, nslots = (226 * 1024 - fixed) / stage;
+      if (fixed + 3 * stage <= 113 * 1024 && 4 * tcols <= 512) {
+        ctas_per_sm = 2;
+        nslots = (113 * 1024 - fixed) / stage;
+      }
+      if (nslots > kWg2MaxSlots) nslots = kWg2MaxSlots;
+      FT3D_REQUIRE(nslots >= 2, "ft3d_conv_wgrad_pairs_tc: tile does not fit shared memory");
+      const int smem_bytes = fixed + nslots * stage;
+      static int configured2 = 0;
+      if (!configured2) {
+        FT3D_CUDA(cudaFuncSetAttribute(conv_wgrad_pairs_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+        configured2 = 1;
+      }
+      const int64_t tiles = (max_pairs + tc::kTileRows - 1) / tc::kTileRows + (pairs ? K : 0);
+      const int64_t units = tiles * ((cin + 127) / 128);
+      const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+      const unsigned grid = (unsigned)(units < cap ? units : cap);
+      conv_wgrad_pairs_tc_v2_kernel<<<grid, kV3Threads, smem_bytes, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs,
+          cin, cout, gw, nslots, tcols, a_blocks);
+      return check_launch("ft3d_conv_wgrad_pairs_tc");
+    }
+  }
   const int stage_bytes = (2 + nb_blocks) * tc::kBlockBytes;
   const int tail = (int)sizeof(WgSmemHeader) + 1024;
   // two resident CTAs when two stages of each fit in half the shared memory, else one CTA with up to 4 stages

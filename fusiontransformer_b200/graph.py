@@ -19,6 +19,8 @@ Results equal the eager exact-shape step (tests/test_gpu_graph.py): padding adds
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -216,7 +218,9 @@ class GraphedStep:
         self.done = None                    # event: the last replay has finished reading the static buffers
         # warm-up and capture share one stream: autograd's AccumulateGrad nodes remember the stream they were created
         # on, and a mismatch during capture would insert an uncapturable cross-stream wait
-        self.stream = torch.cuda.Stream()
+        # priorities: geometry prefetch (-2) > this stream's forward/dgrad chain (-1) > side-stream wgrad (0), so the
+        # short kernels of the dependent chain are scheduled as soon as a wgrad CTA retires instead of behind its grid
+        self.stream = torch.cuda.Stream(priority=int(os.environ.get("FT3D_MAIN_PRIORITY", "-1")))
 
     def _capture(self, plan: GeometryPlan):
         from . import _lib
