@@ -372,6 +372,7 @@ def main():
     if not args.no_roofline:             # every rank runs the pass (the steps contain collectives); rank 0 reports
         pk = peaks()
         L.profile, conv_engine.WORK_LOG = [], []
+        L.profile_repeat = {"conv_pairs_tc": 4}      # idempotent: P is rewritten with the same values
         nprof = min(args.steps, 5)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -381,11 +382,11 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         prof, work = L.profile, conv_engine.WORK_LOG
-        L.profile, conv_engine.WORK_LOG = None, None
+        L.profile, conv_engine.WORK_LOG, L.profile_repeat = None, None, {}
         tot = {}
-        for name, a, b in prof:
+        for name, a, b, reps in prof:
             t = tot.setdefault(name, [0.0, 0])
-            t[0] += a.elapsed_time(b)
+            t[0] += a.elapsed_time(b) / reps
             t[1] += 1
         step_ms = e0.elapsed_time(e1) / nprof
         shares = {k: round(v[0] / nprof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])}
@@ -420,8 +421,9 @@ def main():
                         "tflops": fl / t_s / 1e12, "gbs": by / t_s / 1e9,
                         "share_of_step": tot[dom][0] / nprof / (ms / args.steps),
                         "share_of_kernel_time": tot[dom][0] / max(sum(v[0] for v in tot.values()), 1e-9),
-                        "note": "time = CUDA events around every conv_pairs_tc launch on the launching stream, "
-                                "summed over %d separately profiled steps launched kernel by kernel; share_of_step = that time per "
+                        "note": "time = CUDA events on the launching stream around every conv_pairs_tc call (4 back-to-back "
+                                "launches of it between the two events, / 4: a single ~20 us launch would carry ~8 us "
+                                "of event overhead), summed over %d separately profiled steps launched kernel by kernel; share_of_step = that time per "
                                 "step / the graph-replayed ms_per_step (kernels of other streams overlap it); "
                                 "share_of_kernel_time = / the sum over all libft3d entry points" % nprof}
 

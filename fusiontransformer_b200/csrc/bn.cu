@@ -31,6 +31,7 @@ __device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
 __global__ void __launch_bounds__(kColThreads)
 bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_per_cta,
                 float* __restrict__ partials, const int32_t* __restrict__ valid_rows) {
+  pdl_enter();
   __shared__ float4 s_stage[kColStageFloat4];
   n = effective_rows(n, valid_rows);
   const int ch = threadIdx.x * 4;
@@ -51,6 +52,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, int64_t n, int chan
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ res, int relu, float* __restrict__ z,
                                 __nv_bfloat16* __restrict__ z16, const int32_t* __restrict__ valid_rows) {
+  pdl_enter();
   const int cv = channels >> 2;
   const int64_t total = n * cv;
   const int64_t nv = effective_rows(n, valid_rows);
@@ -100,6 +102,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ gz, const float* __restrict__ y, 
                      const float* __restrict__ z, int64_t n, int channels, int rows_per_cta,
                      const float* __restrict__ stat, float* __restrict__ partials,
                      const int32_t* __restrict__ valid_rows) {
+  pdl_enter();
   __shared__ float4 s_stage[kColStageFloat4];
   n = effective_rows(n, valid_rows);
   const int ch = threadIdx.x * 4;
@@ -125,6 +128,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ gz, const float* _
                                     const float* __restrict__ red, float* __restrict__ gy,
                                     __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres,
                                     const int32_t* __restrict__ valid_rows) {
+  pdl_enter();
   const int cv = channels >> 2;
   const int64_t total = n * cv;
   const int64_t nv = effective_rows(n, valid_rows);
@@ -177,10 +181,9 @@ int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float 
   FT3D_REQUIRE(aligned16(y) && aligned16(workspace), "ft3d_bn_stats: pointers must be 16-byte aligned");
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_stats: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
-  bn_stats_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>(y, n, channels, g.rows_per_cta, (float*)workspace,
+  launch_pdl(bn_stats_kernel, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
                                                                 valid_rows);
-  col_finalize_kernel<0><<<channels / 4, kColThreads, 0, (cudaStream_t)stream>>>(
-      (const float*)workspace, g.grid, channels, n, eps, momentum, stat, running_mean, running_var, 0, valid_rows);
+  launch_pdl(col_finalize_kernel<0>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream, (const float*)workspace, g.grid, channels, n, eps, momentum, stat, running_mean, running_var, 0, valid_rows);
   return check_launch("ft3d_bn_stats");
 }
 
@@ -193,8 +196,7 @@ int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat
   FT3D_REQUIRE(aligned16(y) && aligned16(stat) && aligned16(gamma) && aligned16(beta) && aligned16(res) &&
                    aligned16(z) && ((uintptr_t)z16 & 7) == 0,
                "ft3d_bn_apply: pointers must be 16-byte aligned");
-  bn_apply_kernel<<<grid_for(n * (channels / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      y, n, channels, stat, gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows);
+  launch_pdl(bn_apply_kernel, dim3(grid_for(n * (channels / 4), 256)), dim3(256), 0, (cudaStream_t)stream, y, n, channels, stat, gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows);
   return check_launch("ft3d_bn_apply");
 }
 
@@ -210,10 +212,8 @@ int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const f
                "ft3d_bn_bwd_reduce: pointers must be 16-byte aligned");
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_bwd_reduce: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
-  bn_bwd_reduce_kernel<<<g.grid, g.block, 0, (cudaStream_t)stream>>>(
-      gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows);
-  col_finalize_kernel<1><<<channels / 4, kColThreads, 0, (cudaStream_t)stream>>>(
-      (const float*)workspace, g.grid, channels, n, 0.f, 0.f, red, dgamma, dbeta, accumulate, valid_rows);
+  launch_pdl(bn_bwd_reduce_kernel, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows);
+  launch_pdl(col_finalize_kernel<1>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream, (const float*)workspace, g.grid, channels, n, 0.f, 0.f, red, dgamma, dbeta, accumulate, valid_rows);
   return check_launch("ft3d_bn_bwd_reduce");
 }
 
@@ -226,8 +226,7 @@ int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const fl
   FT3D_REQUIRE(aligned16(gz) && aligned16(y) && aligned16(z) && ((uintptr_t)z16 & 7) == 0 && aligned16(stat) &&
                    aligned16(gamma) && aligned16(red) && aligned16(gy) && ((uintptr_t)gy16 & 7) == 0 && aligned16(gres),
                "ft3d_bn_bwd_apply: pointers must be 16-byte aligned");
-  bn_bwd_apply_kernel<<<grid_for(n * (channels / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      gz, y, (const __nv_bfloat16*)z16, z, n, channels, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows);
+  launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(n * (channels / 4), 256)), dim3(256), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows);
   return check_launch("ft3d_bn_bwd_apply");
 }
 

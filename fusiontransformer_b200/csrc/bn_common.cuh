@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kColThreads)
 col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels, int64_t n, float eps, float momentum,
                     float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2, int accumulate,
                     const int32_t* __restrict__ valid_rows) {
+  pdl_enter();
   __shared__ double s_acc[kColThreads / 32][8];
   n = effective_rows(n, valid_rows);
   if (n < 1) n = 1;

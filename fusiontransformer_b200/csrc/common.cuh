@@ -52,6 +52,37 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL).  Every kernel launched through launch_pdl() starts with pdl_enter():
+// griddepcontrol.wait blocks until the preceding kernel of the stream has completed and flushed, THEN
+// launch_dependents lets the next kernel's CTAs be scheduled and run their prologue while this one executes.  Because
+// a kernel triggers only after its own wait, a dependent that has started knows everything up to its
+// grand-predecessor is complete; it still waits for its predecessor before touching memory.  Launch latency and CTA
+// ramp-up of the ~700 short, strictly dependent kernels of a training step overlap instead of adding up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+bool pdl_enabled();   // FT3D_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops)
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through check_launch()
+}
+
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

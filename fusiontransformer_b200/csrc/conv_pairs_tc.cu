@@ -93,11 +93,17 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
   if (pairs != nullptr) {
     if ((int)threadIdx.x <= K) hdr->off[threadIdx.x] = __ldg(off + threadIdx.x);
     __syncthreads();
-    if (!pair_tile(hdr->off, K, blockIdx.x, kTileRows, &k, &begin, &end)) return;   // uniform per CTA
+    if (!pair_tile(hdr->off, K, blockIdx.x, kTileRows, &k, &begin, &end)) {          // uniform per CTA
+      pdl_wait();
+      return;
+    }
   } else {
     begin = blockIdx.x * kTileRows;
     end = (int)min((int64_t)begin + kTileRows, n_identity);
-    if (begin >= end) return;
+    if (begin >= end) {
+      pdl_wait();
+      return;
+    }
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -126,6 +132,7 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();      // launch, barrier/TMEM set-up and the pair-index loads (static geometry) ran under the predecessor
   const uint32_t tmem_base = hdr->tmem_base;
 
   if (warp < 4) {
@@ -254,7 +261,10 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
   const int chunk = (T + (int)gridDim.x - 1) / (int)gridDim.x;
   const int g0 = (int)blockIdx.x * chunk;
   const int g1 = g0 + chunk < T ? g0 + chunk : T;
-  if (g0 >= g1) return;                                    // uniform per CTA
+  if (g0 >= g1) {                                          // uniform per CTA
+    pdl_wait();
+    return;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
@@ -273,6 +283,7 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();      // launch, schedule, barrier and TMEM set-up ran under the predecessor's tail
   const uint32_t tmem_base = hdr->tmem_base;
 
   auto tile_of = [&](int g, int* k, int* begin, int* end) {
@@ -422,6 +433,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(kColThreads)
 conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos, int64_t n_rows, int kpad, int ncols,
                    int rows_per_cta, float* __restrict__ out, float* __restrict__ partials) {
+  pdl_enter();
   __shared__ float4 s_stage[STATS ? kColStageFloat4 : 1];
   const int ch = threadIdx.x * 4;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -454,6 +466,7 @@ conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos
 // pposT[gather-side row][k] = pair position, for the role-swapped use of a map (dgrad, transposed conv)
 __global__ void pair_positions_kernel(const int2* __restrict__ pairs, const int32_t* __restrict__ off, int K, int kpad,
                                       int col, int32_t* __restrict__ ppos) {
+  pdl_enter();
   __shared__ int32_t s_off[40];
   if ((int)threadIdx.x <= K) s_off[threadIdx.x] = __ldg(off + threadIdx.x);
   __syncthreads();
@@ -468,6 +481,7 @@ __global__ void pair_positions_kernel(const int2* __restrict__ pairs, const int3
 
 // in-place row compaction: valid positions to the front (ascending offset order kept), -1 behind
 __global__ void compact_rows_kernel(int32_t* ppos, int64_t n_rows, int kpad) {
+  pdl_enter();
   for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n_rows; row += (int64_t)gridDim.x * blockDim.x) {
     int4* pr = reinterpret_cast<int4*>(ppos + row * kpad);
     int v[32];
@@ -487,11 +501,13 @@ __global__ void compact_rows_kernel(int32_t* ppos, int64_t n_rows, int kpad) {
 }
 
 __global__ void fill_i32_kernel_p(int32_t* p, int64_t n, int32_t v) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // fp32 -> bf16 (round to nearest even), 8 elements per thread
 __global__ void to_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ dst) {
+  pdl_enter();
   const int64_t n8 = n >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
@@ -534,11 +550,17 @@ conv_wgrad_pairs_tc_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
   if (pairs != nullptr) {
     if ((int)threadIdx.x <= K) hdr->off[threadIdx.x] = __ldg(off + threadIdx.x);
     __syncthreads();
-    if (!pair_tile(hdr->off, K, blockIdx.x, rows_per_cta, &k, &begin, &end)) return;
+    if (!pair_tile(hdr->off, K, blockIdx.x, rows_per_cta, &k, &begin, &end)) {
+      pdl_wait();
+      return;
+    }
   } else {
     begin = blockIdx.x * rows_per_cta;
     end = (int)min((int64_t)begin + rows_per_cta, n_identity);
-    if (begin >= end) return;
+    if (begin >= end) {
+      pdl_wait();
+      return;
+    }
   }
   const int mb = blockIdx.y;
   const int m_valid = cin - mb * 128 < 128 ? cin - mb * 128 : 128;
@@ -571,6 +593,7 @@ conv_wgrad_pairs_tc_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();
   const uint32_t tmem_base = hdr->tmem_base;
 
   if (warp < 4) {
@@ -671,7 +694,10 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
   const int chunk = (U + (int)gridDim.x - 1) / (int)gridDim.x;
   const int u0 = (int)blockIdx.x * chunk;
   const int u1 = u0 + chunk < U ? u0 + chunk : U;
-  if (u0 >= u1) return;                                    // uniform per CTA
+  if (u0 >= u1) {                                          // uniform per CTA
+    pdl_wait();
+    return;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
@@ -688,6 +714,7 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();
   const uint32_t tmem_base = hdr->tmem_base;
 
   auto unit_of = [&](int u, int* mb, int* k, int* begin, int* end) {
@@ -833,7 +860,7 @@ extern "C" {
 int ft3d_to_bf16(const float* src, int64_t n, void* dst, ft3d_stream_t stream) {
   if (n == 0) return FT3D_OK;
   FT3D_REQUIRE(src && dst && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "ft3d_to_bf16: bad arguments");
-  to_bf16_kernel<<<grid_for((n >> 3) + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, n, (__nv_bfloat16*)dst);
+  launch_pdl(to_bf16_kernel, dim3(grid_for((n >> 3) + 1, 256)), dim3(256), 0, (cudaStream_t)stream, src, n, (__nv_bfloat16*)dst);
   return check_launch("ft3d_to_bf16");
 }
 
@@ -843,13 +870,13 @@ int ft3d_kmap_pair_positions(const int32_t* pairs, const int32_t* pair_offsets, 
   FT3D_REQUIRE(K > 0 && K <= kpad && (col == 0 || col == 1), "ft3d_kmap_pair_positions: bad arguments");
   if (n_rows > 0) {
     FT3D_REQUIRE(ppos_out != nullptr, "ft3d_kmap_pair_positions: null output");
-    fill_i32_kernel_p<<<grid_for(n_rows * kpad, 256), 256, 0, s>>>(ppos_out, n_rows * kpad, -1);
+    launch_pdl(fill_i32_kernel_p, dim3(grid_for(n_rows * kpad, 256)), dim3(256), 0, s, ppos_out, n_rows * kpad, -1);
   }
   if (n_rows > 0 && max_pairs > 0) {
     FT3D_REQUIRE(pairs && pair_offsets, "ft3d_kmap_pair_positions: null input");
-    pair_positions_kernel<<<grid_for(max_pairs, 256), 256, 0, s>>>((const int2*)pairs, pair_offsets, K, kpad, col,
+    launch_pdl(pair_positions_kernel, dim3(grid_for(max_pairs, 256)), dim3(256), 0, s, (const int2*)pairs, pair_offsets, K, kpad, col,
                                                                    ppos_out);
-    compact_rows_kernel<<<grid_for(n_rows, 128), 128, 0, s>>>(ppos_out, n_rows, kpad);
+    launch_pdl(compact_rows_kernel, dim3(grid_for(n_rows, 128)), dim3(128), 0, s, ppos_out, n_rows, kpad);
   }
   return check_launch("ft3d_kmap_pair_positions");
 }
@@ -898,8 +925,7 @@ int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t*
       const int64_t tiles = (max_pairs + tc::kTileRows - 1) / tc::kTileRows + (pairs ? K : 0);
       const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
       const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-      conv_pairs_tc_v3_kernel<<<grid, kV3Threads, smem_bytes, (cudaStream_t)stream>>>(
-          (const __nv_bfloat16*)in_bf16, (const int2*)pairs, pair_offsets, K, gather_col, max_pairs, red, ncols,
+      launch_pdl(conv_pairs_tc_v3_kernel, dim3(grid), dim3(kV3Threads), smem_bytes, (cudaStream_t)stream, (const __nv_bfloat16*)in_bf16, (const int2*)pairs, pair_offsets, K, gather_col, max_pairs, red, ncols,
           (const uint8_t*)wpacked, partial_out, nslots, tmem_cols_pow2(ncols));
       return check_launch("ft3d_conv_pairs_tc");
     }
@@ -919,8 +945,7 @@ int ft3d_conv_pairs_tc(const void* in_bf16, const int32_t* pairs, const int32_t*
     configured = 1;
   }
   const int64_t tiles = (max_pairs + tc::kTileRows - 1) / tc::kTileRows + (pairs ? K : 0);
-  conv_pairs_tc_kernel<<<(unsigned)tiles, kPThreads, smem_bytes, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)in_bf16, (const int2*)pairs, pair_offsets, K, gather_col, max_pairs, red, ncols,
+  launch_pdl(conv_pairs_tc_kernel, dim3((unsigned)tiles), dim3(kPThreads), smem_bytes, (cudaStream_t)stream, (const __nv_bfloat16*)in_bf16, (const int2*)pairs, pair_offsets, K, gather_col, max_pairs, red, ncols,
       (const uint8_t*)wpacked, partial_out, nstages, tmem_cols_pow2(ncols));
   return check_launch("ft3d_conv_pairs_tc");
 }
@@ -938,12 +963,12 @@ static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_ro
     FT3D_REQUIRE(stat && workspace && ((uintptr_t)workspace & 15) == 0 &&
                      workspace_bytes >= col_workspace_bytes(ncols) && (running_mean == nullptr) == (running_var == nullptr),
                  "%s: statistics need stat and a workspace of ft3d_bn_workspace(ncols) bytes", what);
-    conv_reduce_kernel<true><<<g.grid, g.block, 0, s>>>(partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
+    launch_pdl(conv_reduce_kernel<true>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
                                                         (float*)workspace);
-    col_finalize_kernel<0><<<ncols / 4, kColThreads, 0, s>>>((const float*)workspace, g.grid, ncols, n_rows, eps, momentum,
+    launch_pdl(col_finalize_kernel<0>, dim3(ncols / 4), dim3(kColThreads), 0, s, (const float*)workspace, g.grid, ncols, n_rows, eps, momentum,
                                                              stat, running_mean, running_var, 0, valid_rows);
   } else {
-    conv_reduce_kernel<false><<<g.grid, g.block, 0, s>>>(partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr);
+    launch_pdl(conv_reduce_kernel<false>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr);
   }
   return check_launch(what);
 }
@@ -1005,8 +1030,7 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
       const int64_t units = tiles * ((cin + 127) / 128);
       const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
       const unsigned grid = (unsigned)(units < cap ? units : cap);
-      conv_wgrad_pairs_tc_v2_kernel<<<grid, kV3Threads, smem_bytes, (cudaStream_t)stream>>>(
-          (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs,
+      launch_pdl(conv_wgrad_pairs_tc_v2_kernel, dim3(grid), dim3(kV3Threads), smem_bytes, (cudaStream_t)stream, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs,
           cin, cout, gw, nslots, tcols, a_blocks);
       return check_launch("ft3d_conv_wgrad_pairs_tc");
     }
@@ -1027,8 +1051,7 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
   const int rows = nst * tc::kTileRows;
   const int64_t items = (max_pairs + rows - 1) / rows + (pairs ? K : 0);
   dim3 grid((unsigned)items, (unsigned)((cin + 127) / 128));
-  conv_wgrad_pairs_tc_kernel<<<grid, kPThreads, smem_bytes, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs, cin,
+  launch_pdl(conv_wgrad_pairs_tc_kernel, dim3(grid), dim3(kPThreads), smem_bytes, (cudaStream_t)stream, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs, cin,
       cout, gw, nst, tmem_cols_pow2(cout));
   return check_launch("ft3d_conv_wgrad_pairs_tc");
 }

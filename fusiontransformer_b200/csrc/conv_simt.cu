@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(128)
 conv_gather_f32_kernel(const float* __restrict__ in, const int32_t* __restrict__ nbr, int64_t n_out, int K,
                        int kpad, int kflip, int red, int ncols, const float* __restrict__ w, int w_transposed,
                        float* __restrict__ out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= n_out) return;
@@ -66,6 +67,7 @@ __device__ __forceinline__ bool wgrad_item(const int32_t* __restrict__ off, int 
 __global__ void __launch_bounds__(256)
 conv_wgrad_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, const int2* __restrict__ pairs,
                       const int32_t* __restrict__ off, int K, int ca, int cin, int cout, float* __restrict__ gw) {
+  pdl_enter();
   __shared__ int s_a[kWgradChunk], s_b[kWgradChunk];
   int k, begin, end;
   if (!wgrad_item(off, K, kWgradChunk, blockIdx.x, &k, &begin, &end)) return;
@@ -99,8 +101,7 @@ int ft3d_conv_gather_f32(const float* in, const int32_t* nbr, int64_t n_out, int
   FT3D_REQUIRE(in && nbr && w && out, "ft3d_conv_gather_f32: null pointer");
   FT3D_REQUIRE(K > 0 && K <= kpad && red > 0 && ncols > 0 && ncols <= 32 * kMaxColsPerLane,
                "ft3d_conv_gather_f32: unsupported shape K=%d kpad=%d red=%d ncols=%d", K, kpad, red, ncols);
-  conv_gather_f32_kernel<<<(unsigned)((n_out + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
-      in, nbr, n_out, K, kpad, kflip, red, ncols, w, w_transposed, out);
+  launch_pdl(conv_gather_f32_kernel, dim3((unsigned)((n_out + 3) / 4)), dim3(128), 0, (cudaStream_t)stream, in, nbr, n_out, K, kpad, kflip, red, ncols, w, w_transposed, out);
   return check_launch("ft3d_conv_gather_f32");
 }
 
@@ -111,7 +112,7 @@ int ft3d_conv_wgrad_f32(const float* a, const float* b, const int32_t* pairs, co
   FT3D_REQUIRE(a && b && pairs && pair_offsets && gw && K > 0 && cin > 0 && cout > 0,
                "ft3d_conv_wgrad_f32: bad arguments");
   int64_t items = (max_pairs + kWgradChunk - 1) / kWgradChunk + K;
-  conv_wgrad_f32_kernel<<<(unsigned)items, 256, 0, (cudaStream_t)stream>>>(a, b, (const int2*)pairs, pair_offsets,
+  launch_pdl(conv_wgrad_f32_kernel, dim3((unsigned)items), dim3(256), 0, (cudaStream_t)stream, a, b, (const int2*)pairs, pair_offsets,
                                                                             K, ca, cin, cout, gw);
   return check_launch("ft3d_conv_wgrad_f32");
 }

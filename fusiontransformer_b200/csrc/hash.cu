@@ -1,6 +1,7 @@
 // Hashing, coordinate scaling and the open-addressing coordinate table (K1, K2, K3, a1).
 // All kernels are HBM/L2-bound integer work: one element per thread, 16-byte coordinate loads,
 // grid-stride loops sized in multiples of the SM count.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ft3d {
@@ -12,6 +13,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FT3D_PDL");
+    on = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return on != 0;
 }
 
 // ------------------------------------------------------------------ K1

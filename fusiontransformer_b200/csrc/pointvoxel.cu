@@ -6,6 +6,7 @@
 namespace ft3d {
 
 __global__ void zero_f32_kernel(float* __restrict__ p, int64_t n) {
+  pdl_enter();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t n4 = n >> 2;
@@ -15,11 +16,13 @@ __global__ void zero_f32_kernel(float* __restrict__ p, int64_t n) {
 }
 
 __global__ void zero_i32_kernel2(int32_t* __restrict__ p, int64_t n) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
 }
 
 // ------------------------------------------------------------------ K5
 __global__ void count_kernel(const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ cnt, int64_t m) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int v = idx[i];
     if (v >= 0 && v < m) atomicAdd(cnt + v, 1);
@@ -31,6 +34,7 @@ template <int VEC>
 __global__ void voxelize_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
                                     const int32_t* __restrict__ cnt, int64_t n, int64_t m, int c,
                                     float* __restrict__ out) {
+  pdl_enter();
   const int cv = c / VEC;
   int64_t total = n * cv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -54,6 +58,7 @@ template <int VEC>
 __global__ void voxelize_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx,
                                     const int32_t* __restrict__ cnt, int64_t n, int64_t m, int c,
                                     float* __restrict__ gin) {
+  pdl_enter();
   const int cv = c / VEC;
   int64_t total = n * cv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -77,6 +82,7 @@ template <int VEC>
 __global__ void devoxelize_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx,
                                       const float* __restrict__ w, int64_t n, int64_t m, int c,
                                       float* __restrict__ out) {
+  pdl_enter();
   const int cv = c / VEC;
   int64_t total = n * cv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -107,6 +113,7 @@ template <int VEC>
 __global__ void devoxelize_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx,
                                       const float* __restrict__ w, int64_t n, int64_t m, int c,
                                       float* __restrict__ gfeat) {
+  pdl_enter();
   const int cv = c / VEC;
   int64_t total = n * cv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -143,6 +150,7 @@ __device__ __forceinline__ float ti_weight(float x, float y, float z, float scal
 
 __global__ void ti_weights_kernel(const float4* __restrict__ pc, const int64_t* __restrict__ idx, int64_t n,
                                   float scale, float* __restrict__ w_out) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float4 p = __ldg(pc + i);
     float wk[8];
@@ -163,6 +171,7 @@ __global__ void ti_weights_kernel(const float4* __restrict__ pc, const int64_t* 
 __global__ void v2p_build_kernel(const float4* __restrict__ pc, int64_t n, int stride,
                                  const unsigned long long* __restrict__ tkeys, const int* __restrict__ tvals,
                                  uint32_t mask, int32_t* __restrict__ idx_out, float* __restrict__ w_out) {
+  pdl_enter();
   const float scale = (float)stride;
   int64_t total = n * 8;
   int64_t padded = (total + 31) / 32 * 32;
@@ -196,6 +205,7 @@ __global__ void v2p_build_kernel(const float4* __restrict__ pc, int64_t n, int s
 __global__ void p2v_build_kernel(const float4* __restrict__ pc, int64_t n, int stride,
                                  const unsigned long long* __restrict__ tkeys, const int* __restrict__ tvals,
                                  uint32_t mask, int32_t* __restrict__ idx_out, int32_t* __restrict__ cnt, int64_t m) {
+  pdl_enter();
   const float scale = (float)stride;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float4 p = __ldg(pc + i);
@@ -213,6 +223,7 @@ template <int VEC>
 __global__ void lift_fwd_kernel(const float* __restrict__ fmap, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
                                 int B, int C, int H, int W, const int2* __restrict__ rc,
                                 const int32_t* __restrict__ bidx, int64_t n, float* __restrict__ out) {
+  pdl_enter();
   const int cv = C / VEC;
   int64_t total = n * cv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -231,6 +242,7 @@ template <int VEC>
 __global__ void lift_bwd_kernel(const float* __restrict__ gout, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
                                 int B, int C, int H, int W, const int2* __restrict__ rc,
                                 const int32_t* __restrict__ bidx, int64_t n, float* __restrict__ gmap) {
+  pdl_enter();
   const int cv = C / VEC;
   int64_t total = n * cv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -251,8 +263,8 @@ using namespace ft3d;
 
 #define LAUNCH_VEC(kernel, c, n, s, ...)                                                     \
   do {                                                                                       \
-    if ((c) % 4 == 0) kernel<4><<<grid_for((n) * ((c) / 4), 256), 256, 0, s>>>(__VA_ARGS__); \
-    else kernel<1><<<grid_for((n) * (c), 256), 256, 0, s>>>(__VA_ARGS__);                    \
+    if ((c) % 4 == 0) launch_pdl(kernel<4>, dim3(grid_for((n) * ((c) / 4), 256)), dim3(256), 0, s, __VA_ARGS__); \
+    else launch_pdl(kernel<1>, dim3(grid_for((n) * (c), 256)), dim3(256), 0, s, __VA_ARGS__);                    \
   } while (0)
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -263,11 +275,11 @@ int ft3d_count(const int32_t* idx, int64_t n, int32_t* cnt_out, int64_t m, ft3d_
   cudaStream_t s = (cudaStream_t)stream;
   if (m > 0) {
     FT3D_REQUIRE(cnt_out != nullptr, "ft3d_count: null output");
-    zero_i32_kernel2<<<grid_for(m, 256), 256, 0, s>>>(cnt_out, m);
+    launch_pdl(zero_i32_kernel2, dim3(grid_for(m, 256)), dim3(256), 0, s, cnt_out, m);
   }
   if (n > 0 && m > 0) {
     FT3D_REQUIRE(idx != nullptr, "ft3d_count: null idx");
-    count_kernel<<<grid_for(n, 256), 256, 0, s>>>(idx, n, cnt_out, m);
+    launch_pdl(count_kernel, dim3(grid_for(n, 256)), dim3(256), 0, s, idx, n, cnt_out, m);
   }
   return check_launch("ft3d_count");
 }
@@ -278,12 +290,12 @@ int ft3d_voxelize_fwd(const float* feat, const int32_t* idx, const int32_t* cnt,
   FT3D_REQUIRE(c > 0, "ft3d_voxelize_fwd: c must be positive");
   if (m > 0) {
     FT3D_REQUIRE(out != nullptr, "ft3d_voxelize_fwd: null output");
-    zero_f32_kernel<<<grid_for(m * c / 4 + 1, 256), 256, 0, s>>>(out, m * c);
+    launch_pdl(zero_f32_kernel, dim3(grid_for(m * c / 4 + 1, 256)), dim3(256), 0, s, out, m * c);
   }
   if (n > 0 && m > 0) {
     FT3D_REQUIRE(feat && idx && cnt, "ft3d_voxelize_fwd: null input");
-    if (c % 4 == 0 && aligned16(feat) && aligned16(out)) voxelize_fwd_kernel<4><<<grid_for(n * (c / 4), 256), 256, 0, s>>>(feat, idx, cnt, n, m, c, out);
-    else voxelize_fwd_kernel<1><<<grid_for(n * c, 256), 256, 0, s>>>(feat, idx, cnt, n, m, c, out);
+    if (c % 4 == 0 && aligned16(feat) && aligned16(out)) launch_pdl(voxelize_fwd_kernel<4>, dim3(grid_for(n * (c / 4), 256)), dim3(256), 0, s, feat, idx, cnt, n, m, c, out);
+    else launch_pdl(voxelize_fwd_kernel<1>, dim3(grid_for(n * c, 256)), dim3(256), 0, s, feat, idx, cnt, n, m, c, out);
   }
   return check_launch("ft3d_voxelize_fwd");
 }
@@ -294,9 +306,9 @@ int ft3d_voxelize_bwd(const float* gout, const int32_t* idx, const int32_t* cnt,
   if (n == 0) return FT3D_OK;
   FT3D_REQUIRE(gout && idx && cnt && gin && c > 0, "ft3d_voxelize_bwd: bad arguments");
   if (c % 4 == 0 && aligned16(gout) && aligned16(gin))
-    voxelize_bwd_kernel<4><<<grid_for(n * (c / 4), 256), 256, 0, s>>>(gout, idx, cnt, n, m, c, gin);
+    launch_pdl(voxelize_bwd_kernel<4>, dim3(grid_for(n * (c / 4), 256)), dim3(256), 0, s, gout, idx, cnt, n, m, c, gin);
   else
-    voxelize_bwd_kernel<1><<<grid_for(n * c, 256), 256, 0, s>>>(gout, idx, cnt, n, m, c, gin);
+    launch_pdl(voxelize_bwd_kernel<1>, dim3(grid_for(n * c, 256)), dim3(256), 0, s, gout, idx, cnt, n, m, c, gin);
   return check_launch("ft3d_voxelize_bwd");
 }
 
@@ -306,9 +318,9 @@ int ft3d_devoxelize_fwd(const float* feat, const int32_t* idx, const float* w, i
   if (n == 0) return FT3D_OK;
   FT3D_REQUIRE(idx && w && out && c > 0 && (feat || m == 0), "ft3d_devoxelize_fwd: bad arguments");
   if (c % 4 == 0 && aligned16(feat) && aligned16(out))
-    devoxelize_fwd_kernel<4><<<grid_for(n * (c / 4), 256), 256, 0, s>>>(feat, idx, w, n, m, c, out);
+    launch_pdl(devoxelize_fwd_kernel<4>, dim3(grid_for(n * (c / 4), 256)), dim3(256), 0, s, feat, idx, w, n, m, c, out);
   else
-    devoxelize_fwd_kernel<1><<<grid_for(n * c, 256), 256, 0, s>>>(feat, idx, w, n, m, c, out);
+    launch_pdl(devoxelize_fwd_kernel<1>, dim3(grid_for(n * c, 256)), dim3(256), 0, s, feat, idx, w, n, m, c, out);
   return check_launch("ft3d_devoxelize_fwd");
 }
 
@@ -318,14 +330,14 @@ int ft3d_devoxelize_bwd(const float* gout, const int32_t* idx, const float* w, i
   FT3D_REQUIRE(c > 0, "ft3d_devoxelize_bwd: c must be positive");
   if (m > 0) {
     FT3D_REQUIRE(gfeat != nullptr, "ft3d_devoxelize_bwd: null output");
-    zero_f32_kernel<<<grid_for(m * c / 4 + 1, 256), 256, 0, s>>>(gfeat, m * c);
+    launch_pdl(zero_f32_kernel, dim3(grid_for(m * c / 4 + 1, 256)), dim3(256), 0, s, gfeat, m * c);
   }
   if (n > 0 && m > 0) {
     FT3D_REQUIRE(gout && idx && w, "ft3d_devoxelize_bwd: null input");
     if (c % 4 == 0 && aligned16(gout) && aligned16(gfeat))
-      devoxelize_bwd_kernel<4><<<grid_for(n * (c / 4), 256), 256, 0, s>>>(gout, idx, w, n, m, c, gfeat);
+      launch_pdl(devoxelize_bwd_kernel<4>, dim3(grid_for(n * (c / 4), 256)), dim3(256), 0, s, gout, idx, w, n, m, c, gfeat);
     else
-      devoxelize_bwd_kernel<1><<<grid_for(n * c, 256), 256, 0, s>>>(gout, idx, w, n, m, c, gfeat);
+      launch_pdl(devoxelize_bwd_kernel<1>, dim3(grid_for(n * c, 256)), dim3(256), 0, s, gout, idx, w, n, m, c, gfeat);
   }
   return check_launch("ft3d_devoxelize_bwd");
 }
@@ -334,7 +346,7 @@ int ft3d_ti_weights(const float* pc, const int64_t* idx, int64_t n, float scale,
                     ft3d_stream_t stream) {
   if (n == 0) return FT3D_OK;
   FT3D_REQUIRE(pc && idx && w_out && scale > 0.f && aligned16(pc), "ft3d_ti_weights: bad arguments");
-  ti_weights_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)pc, idx, n, scale, w_out);
+  launch_pdl(ti_weights_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)pc, idx, n, scale, w_out);
   return check_launch("ft3d_ti_weights");
 }
 
@@ -344,8 +356,7 @@ int ft3d_v2p_build(const float* pc, int64_t n, int32_t stride, const uint64_t* t
   if (n == 0) return FT3D_OK;
   FT3D_REQUIRE(pc && table_keys && table_vals && idx_out && w_out && stride > 0 && aligned16(pc) &&
                cap >= 2 && (cap & (cap - 1)) == 0, "ft3d_v2p_build: bad arguments");
-  v2p_build_kernel<<<grid_for(n * 8, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)pc, n, stride, (const unsigned long long*)table_keys, table_vals, (uint32_t)(cap - 1),
+  launch_pdl(v2p_build_kernel, dim3(grid_for(n * 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)pc, n, stride, (const unsigned long long*)table_keys, table_vals, (uint32_t)(cap - 1),
       idx_out, w_out);
   return check_launch("ft3d_v2p_build");
 }
@@ -356,12 +367,12 @@ int ft3d_p2v_build(const float* pc, int64_t n, int32_t stride, const uint64_t* t
   cudaStream_t s = (cudaStream_t)stream;
   if (m > 0) {
     FT3D_REQUIRE(cnt_out != nullptr, "ft3d_p2v_build: null counts");
-    zero_i32_kernel2<<<grid_for(m, 256), 256, 0, s>>>(cnt_out, m);
+    launch_pdl(zero_i32_kernel2, dim3(grid_for(m, 256)), dim3(256), 0, s, cnt_out, m);
   }
   if (n > 0) {
     FT3D_REQUIRE(pc && table_keys && table_vals && idx_out && stride > 0 && aligned16(pc) && cap >= 2 &&
                  (cap & (cap - 1)) == 0, "ft3d_p2v_build: bad arguments");
-    p2v_build_kernel<<<grid_for(n, 256), 256, 0, s>>>((const float4*)pc, n, stride,
+    launch_pdl(p2v_build_kernel, dim3(grid_for(n, 256)), dim3(256), 0, s, (const float4*)pc, n, stride,
                                                       (const unsigned long long*)table_keys, table_vals,
                                                       (uint32_t)(cap - 1), idx_out, cnt_out, m);
   }
@@ -376,9 +387,9 @@ int ft3d_lift_fwd(const float* fmap, int64_t sb, int64_t sc, int64_t sh, int64_t
   cudaStream_t s = (cudaStream_t)stream;
   bool vec = (sc == 1) && (C % 4 == 0) && aligned16(fmap) && aligned16(out) && (sb % 4 == 0) && (sh % 4 == 0) &&
              (sw % 4 == 0);
-  if (vec) lift_fwd_kernel<4><<<grid_for(n * (C / 4), 256), 256, 0, s>>>(fmap, sb, sc, sh, sw, B, C, H, W,
+  if (vec) launch_pdl(lift_fwd_kernel<4>, dim3(grid_for(n * (C / 4), 256)), dim3(256), 0, s, fmap, sb, sc, sh, sw, B, C, H, W,
                                                                         (const int2*)rc, bidx, n, out);
-  else lift_fwd_kernel<1><<<grid_for(n * C, 256), 256, 0, s>>>(fmap, sb, sc, sh, sw, B, C, H, W, (const int2*)rc,
+  else launch_pdl(lift_fwd_kernel<1>, dim3(grid_for(n * C, 256)), dim3(256), 0, s, fmap, sb, sc, sh, sw, B, C, H, W, (const int2*)rc,
                                                               bidx, n, out);
   return check_launch("ft3d_lift_fwd");
 }
@@ -391,9 +402,9 @@ int ft3d_lift_bwd(const float* gout, int64_t sb, int64_t sc, int64_t sh, int64_t
   cudaStream_t s = (cudaStream_t)stream;
   bool vec = (sc == 1) && (C % 4 == 0) && aligned16(gmap) && aligned16(gout) && (sb % 4 == 0) && (sh % 4 == 0) &&
              (sw % 4 == 0);
-  if (vec) lift_bwd_kernel<4><<<grid_for(n * (C / 4), 256), 256, 0, s>>>(gout, sb, sc, sh, sw, B, C, H, W,
+  if (vec) launch_pdl(lift_bwd_kernel<4>, dim3(grid_for(n * (C / 4), 256)), dim3(256), 0, s, gout, sb, sc, sh, sw, B, C, H, W,
                                                                         (const int2*)rc, bidx, n, gmap);
-  else lift_bwd_kernel<1><<<grid_for(n * C, 256), 256, 0, s>>>(gout, sb, sc, sh, sw, B, C, H, W, (const int2*)rc,
+  else launch_pdl(lift_bwd_kernel<1>, dim3(grid_for(n * C, 256)), dim3(256), 0, s, gout, sb, sc, sh, sw, B, C, H, W, (const int2*)rc,
                                                               bidx, n, gmap);
   return check_launch("ft3d_lift_bwd");
 }

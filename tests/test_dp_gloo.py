@@ -45,7 +45,8 @@ def _worker(rank, world, port, q):
     loss.backward()
     launched_in_backward = sum(sync._launched)
     sync.finish()
-    q.put((rank, [p.grad.clone() for p in net.parameters()], [p.data.clone() for p in net.parameters()],
+    # numpy arrays are pickled by value; torch tensors would travel as shared-memory handles that die with the worker
+    q.put((rank, [p.grad.clone().numpy() for p in net.parameters()], [p.data.clone().numpy() for p in net.parameters()],
            launched_in_backward, len(sync.buckets), idx))
     dist.barrier()
     dist.destroy_process_group()
@@ -62,6 +63,7 @@ def test_gradsync_world2_matches_full_batch():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [(r, [torch.from_numpy(a) for a in g], [torch.from_numpy(a) for a in w], l, nb, i) for r, g, w, l, nb, i in res]
     (r0, g0, w0, l0, nb0, i0), (r1, g1, w1, l1, nb1, i1) = res
     assert sorted(i0 + i1) == list(range(8))
     for a, b in zip(w0, w1):
