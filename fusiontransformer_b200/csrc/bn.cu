@@ -28,6 +28,7 @@ __device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
 }
 
 // ------------------------------------------------------------------------------------------------ statistics
+template <int RB>
 __global__ void __launch_bounds__(kColThreads)
 bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_per_cta,
                 float* __restrict__ partials, const int32_t* __restrict__ valid_rows) {
@@ -38,47 +39,69 @@ bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_p
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  for (int64_t r = row0 + threadIdx.y; r < row1; r += blockDim.y) {
-    const float4 v = ld4(y + r * channels + ch);
-    add4(s1, v);
-    fma4(s2, v, v);
+  const int64_t rstep = blockDim.y;
+  for (int64_t r = row0 + threadIdx.y; r < row1; r += RB * rstep) {      // four independent row loads in flight
+    float4 v[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+      v[i] = r + i * rstep < row1 ? ld4(y + (r + i * rstep) * channels + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      add4(s1, v[i]);
+      fma4(s2, v[i], v[i]);
+    }
   }
   col_publish(s1, s2, partials, channels, s_stage);
 }
 
 // ------------------------------------------------------------------------------------------------ forward apply
 // z = [relu]( (y - mean) * rstd * gamma + beta [+ res] );  writes z (fp32, nullable) and z16 (bf16, nullable).
-__global__ void bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, const float* __restrict__ stat,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ res, int relu, float* __restrict__ z,
-                                __nv_bfloat16* __restrict__ z16, const int32_t* __restrict__ valid_rows) {
+// Same 2-D thread layout as the reductions (a thread owns 4 channels: its statistics and affine parameters are loaded
+// once) and four rows in flight per thread.
+template <int RB>
+__global__ void __launch_bounds__(kColThreads)
+bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_per_cta, const float* __restrict__ stat,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res,
+                int relu, float* __restrict__ z, __nv_bfloat16* __restrict__ z16,
+                const int32_t* __restrict__ valid_rows) {
   pdl_enter();
-  const int cv = channels >> 2;
-  const int64_t total = n * cv;
   const int64_t nv = effective_rows(n, valid_rows);
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = t / cv;
-    const int ch = (int)(t - row * cv) << 2;
-    if (row >= nv) {                      // padding rows of a capacity-sized activation stay exactly zero
-      if (z != nullptr) *reinterpret_cast<float4*>(z + row * channels + ch) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (z16 != nullptr) *reinterpret_cast<uint2*>(z16 + row * channels + ch) = make_uint2(0u, 0u);
-      continue;
+  const int ch = threadIdx.x * 4;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
+  const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), g = ld4(gamma + ch), b = ld4(beta + ch);
+  const float4 sc = make_float4(rs.x * g.x, rs.y * g.y, rs.z * g.z, rs.w * g.w);
+  const int64_t rstep = blockDim.y;
+  for (int64_t r = row0 + threadIdx.y; r < row1; r += RB * rstep) {
+    float4 v[RB], rr[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t row = r + i * rstep;
+      const bool live = row < row1 && row < nv;
+      v[i] = live ? ld4(y + row * channels + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rr[i] = (live && res != nullptr) ? ld4(res + row * channels + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float4 v = ld4(y + row * channels + ch);
-    const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), g = ld4(gamma + ch), b = ld4(beta + ch);
-    float4 o;
-    o.x = fmaf((v.x - m.x) * rs.x, g.x, b.x);
-    o.y = fmaf((v.y - m.y) * rs.y, g.y, b.y);
-    o.z = fmaf((v.z - m.z) * rs.z, g.z, b.z);
-    o.w = fmaf((v.w - m.w) * rs.w, g.w, b.w);
-    if (res != nullptr) add4(o, ld4(res + row * channels + ch));
-    if (relu) {
-      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t row = r + i * rstep;
+      if (row >= row1) break;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);         // padding rows of a capacity-sized activation stay exactly zero
+      if (row < nv) {
+        o.x = fmaf((v[i].x - m.x) * rs.x, g.x, b.x);
+        o.y = fmaf((v[i].y - m.y) * rs.y, g.y, b.y);
+        o.z = fmaf((v[i].z - m.z) * rs.z, g.z, b.z);
+        o.w = fmaf((v[i].w - m.w) * rs.w, g.w, b.w);
+        if (res != nullptr) add4(o, rr[i]);
+        if (relu) {
+          o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+      }
+      if (z != nullptr) *reinterpret_cast<float4*>(z + row * channels + ch) = o;
+      if (z16 != nullptr)
+        *reinterpret_cast<uint2*>(z16 + row * channels + ch) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
-    if (z != nullptr) *reinterpret_cast<float4*>(z + row * channels + ch) = o;
-    if (z16 != nullptr)
-      *reinterpret_cast<uint2*>(z16 + row * channels + ch) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
   }
+  (void)sc;
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -97,6 +120,7 @@ __device__ __forceinline__ float4 masked_grad(const float* __restrict__ gz, cons
 }
 
 // red = [c1[C], c2[C]] = [sum g'/n, sum g'*xhat/n];  dgamma = sum g'*xhat;  dbeta = sum g'
+template <int RB>
 __global__ void __launch_bounds__(kColThreads)
 bn_bwd_reduce_kernel(const float* __restrict__ gz, const float* __restrict__ y, const __nv_bfloat16* __restrict__ z16,
                      const float* __restrict__ z, int64_t n, int channels, int rows_per_cta,
@@ -110,54 +134,79 @@ bn_bwd_reduce_kernel(const float* __restrict__ gz, const float* __restrict__ y, 
   const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
   const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  for (int64_t r = row0 + threadIdx.y; r < row1; r += blockDim.y) {
-    const int64_t off = r * channels + ch;
-    const float4 g = masked_grad(gz, z16, z, off);
-    const float4 v = ld4(y + off);
-    const float4 xh = make_float4((v.x - m.x) * rs.x, (v.y - m.y) * rs.y, (v.z - m.z) * rs.z, (v.w - m.w) * rs.w);
-    add4(s1, g);
-    fma4(s2, g, xh);
+  const int64_t rstep = blockDim.y;
+  for (int64_t r = row0 + threadIdx.y; r < row1; r += RB * rstep) {      // 4 rows x (gz, mask, y) requested together
+    float4 g[RB], v[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t rr = r + i * rstep < row1 ? r + i * rstep : r;     // tail lanes re-read row r and are discarded
+      const int64_t off = rr * channels + ch;
+      g[i] = masked_grad(gz, z16, z, off);
+      v[i] = ld4(y + off);
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      if (r + i * rstep >= row1) break;
+      const float4 xh = make_float4((v[i].x - m.x) * rs.x, (v[i].y - m.y) * rs.y, (v[i].z - m.z) * rs.z,
+                                    (v[i].w - m.w) * rs.w);
+      add4(s1, g[i]);
+      fma4(s2, g[i], xh);
+    }
   }
   col_publish(s1, s2, partials, channels, s_stage);
 }
 
 // gy = gamma * rstd * (g' - c1 - xhat * c2)   (training);   gy = gamma * rstd * g'   (frozen statistics: red == null)
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ gz, const float* __restrict__ y,
-                                    const __nv_bfloat16* __restrict__ z16, const float* __restrict__ z, int64_t n,
-                                    int channels, const float* __restrict__ stat, const float* __restrict__ gamma,
-                                    const float* __restrict__ red, float* __restrict__ gy,
-                                    __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres,
-                                    const int32_t* __restrict__ valid_rows) {
+template <int RB>
+__global__ void __launch_bounds__(kColThreads)
+bn_bwd_apply_kernel(const float* __restrict__ gz, const float* __restrict__ y, const __nv_bfloat16* __restrict__ z16,
+                    const float* __restrict__ z, int64_t n, int channels, int rows_per_cta,
+                    const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ red,
+                    float* __restrict__ gy, __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres,
+                    const int32_t* __restrict__ valid_rows) {
   pdl_enter();
-  const int cv = channels >> 2;
-  const int64_t total = n * cv;
   const int64_t nv = effective_rows(n, valid_rows);
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = t / cv;
-    const int ch = (int)(t - row * cv) << 2;
-    const int64_t off = row * channels + ch;
-    if (row >= nv) {                      // padding rows carry no gradient
-      if (gy != nullptr) *reinterpret_cast<float4*>(gy + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy16 != nullptr) *reinterpret_cast<uint2*>(gy16 + off) = make_uint2(0u, 0u);
-      if (gres != nullptr) *reinterpret_cast<float4*>(gres + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
+  const int ch = threadIdx.x * 4;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
+  const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), ga = ld4(gamma + ch);
+  float4 c1 = make_float4(0.f, 0.f, 0.f, 0.f), c2 = c1;
+  if (red != nullptr) {
+    c1 = ld4(red + ch);
+    c2 = ld4(red + channels + ch);
+  }
+  const int64_t rstep = blockDim.y;
+  for (int64_t r = row0 + threadIdx.y; r < row1; r += RB * rstep) {
+    float4 g[RB], v[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t row = r + i * rstep;
+      const int64_t rr = (row < row1 && row < nv) ? row : (r < nv ? r : 0);   // dead lanes re-read a live row
+      const int64_t off = rr * channels + ch;
+      g[i] = masked_grad(gz, z16, z, off);
+      v[i] = red != nullptr ? ld4(y + off) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float4 g = masked_grad(gz, z16, z, off);
-    const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), ga = ld4(gamma + ch);
-    float4 o;
-    if (red != nullptr) {
-      const float4 v = ld4(y + off);
-      const float4 c1 = ld4(red + ch), c2 = ld4(red + channels + ch);
-      o.x = ga.x * rs.x * (g.x - c1.x - (v.x - m.x) * rs.x * c2.x);
-      o.y = ga.y * rs.y * (g.y - c1.y - (v.y - m.y) * rs.y * c2.y);
-      o.z = ga.z * rs.z * (g.z - c1.z - (v.z - m.z) * rs.z * c2.z);
-      o.w = ga.w * rs.w * (g.w - c1.w - (v.w - m.w) * rs.w * c2.w);
-    } else {
-      o = make_float4(ga.x * rs.x * g.x, ga.y * rs.y * g.y, ga.z * rs.z * g.z, ga.w * rs.w * g.w);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t row = r + i * rstep;
+      if (row >= row1) break;
+      const int64_t off = row * channels + ch;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f), gg = o;     // padding rows carry no gradient
+      if (row < nv) {
+        gg = g[i];
+        if (red != nullptr) {
+          o.x = ga.x * rs.x * (gg.x - c1.x - (v[i].x - m.x) * rs.x * c2.x);
+          o.y = ga.y * rs.y * (gg.y - c1.y - (v[i].y - m.y) * rs.y * c2.y);
+          o.z = ga.z * rs.z * (gg.z - c1.z - (v[i].z - m.z) * rs.z * c2.z);
+          o.w = ga.w * rs.w * (gg.w - c1.w - (v[i].w - m.w) * rs.w * c2.w);
+        } else {
+          o = make_float4(ga.x * rs.x * gg.x, ga.y * rs.y * gg.y, ga.z * rs.z * gg.z, ga.w * rs.w * gg.w);
+        }
+      }
+      if (gy != nullptr) *reinterpret_cast<float4*>(gy + off) = o;
+      if (gy16 != nullptr) *reinterpret_cast<uint2*>(gy16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      if (gres != nullptr) *reinterpret_cast<float4*>(gres + off) = gg;
     }
-    if (gy != nullptr) *reinterpret_cast<float4*>(gy + off) = o;
-    if (gy16 != nullptr) *reinterpret_cast<uint2*>(gy16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-    if (gres != nullptr) *reinterpret_cast<float4*>(gres + off) = g;
   }
 }
 
@@ -181,8 +230,14 @@ int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float 
   FT3D_REQUIRE(aligned16(y) && aligned16(workspace), "ft3d_bn_stats: pointers must be 16-byte aligned");
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_stats: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
-  launch_pdl(bn_stats_kernel, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
-                                                                valid_rows);
+  switch (row_batch()) {
+    case 1: launch_pdl(bn_stats_kernel<1>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
+                                                                valid_rows); break;
+    case 2: launch_pdl(bn_stats_kernel<2>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
+                                                                valid_rows); break;
+    default: launch_pdl(bn_stats_kernel<4>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
+                                                                valid_rows); break;
+  }
   launch_pdl(col_finalize_kernel<0>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream, (const float*)workspace, g.grid, channels, n, eps, momentum, stat, running_mean, running_var, 0, valid_rows);
   return check_launch("ft3d_bn_stats");
 }
@@ -196,7 +251,16 @@ int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat
   FT3D_REQUIRE(aligned16(y) && aligned16(stat) && aligned16(gamma) && aligned16(beta) && aligned16(res) &&
                    aligned16(z) && ((uintptr_t)z16 & 7) == 0,
                "ft3d_bn_apply: pointers must be 16-byte aligned");
-  launch_pdl(bn_apply_kernel, dim3(grid_for(n * (channels / 4), 256)), dim3(256), 0, (cudaStream_t)stream, y, n, channels, stat, gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows);
+  FT3D_REQUIRE(channels <= 1024, "ft3d_bn_apply: at most 1024 channels");
+  ColGrid ga = col_grid(n, channels / 4);
+  switch (row_batch()) {
+    case 1: launch_pdl(bn_apply_kernel<1>, dim3(ga.grid), ga.block, 0, (cudaStream_t)stream, y, n, channels, ga.rows_per_cta, stat,
+             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows); break;
+    case 2: launch_pdl(bn_apply_kernel<2>, dim3(ga.grid), ga.block, 0, (cudaStream_t)stream, y, n, channels, ga.rows_per_cta, stat,
+             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows); break;
+    default: launch_pdl(bn_apply_kernel<4>, dim3(ga.grid), ga.block, 0, (cudaStream_t)stream, y, n, channels, ga.rows_per_cta, stat,
+             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows); break;
+  }
   return check_launch("ft3d_bn_apply");
 }
 
@@ -212,7 +276,11 @@ int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const f
                "ft3d_bn_bwd_reduce: pointers must be 16-byte aligned");
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_bwd_reduce: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
-  launch_pdl(bn_bwd_reduce_kernel, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows);
+  switch (row_batch()) {
+    case 1: launch_pdl(bn_bwd_reduce_kernel<1>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows); break;
+    case 2: launch_pdl(bn_bwd_reduce_kernel<2>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows); break;
+    default: launch_pdl(bn_bwd_reduce_kernel<4>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows); break;
+  }
   launch_pdl(col_finalize_kernel<1>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream, (const float*)workspace, g.grid, channels, n, 0.f, 0.f, red, dgamma, dbeta, accumulate, valid_rows);
   return check_launch("ft3d_bn_bwd_reduce");
 }
@@ -226,7 +294,16 @@ int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const fl
   FT3D_REQUIRE(aligned16(gz) && aligned16(y) && aligned16(z) && ((uintptr_t)z16 & 7) == 0 && aligned16(stat) &&
                    aligned16(gamma) && aligned16(red) && aligned16(gy) && ((uintptr_t)gy16 & 7) == 0 && aligned16(gres),
                "ft3d_bn_bwd_apply: pointers must be 16-byte aligned");
-  launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(n * (channels / 4), 256)), dim3(256), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows);
+  FT3D_REQUIRE(channels <= 1024, "ft3d_bn_bwd_apply: at most 1024 channels");
+  ColGrid gb = col_grid(n, channels / 4);
+  switch (row_batch()) {
+    case 1: launch_pdl(bn_bwd_apply_kernel<1>, dim3(gb.grid), gb.block, 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z,
+             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows); break;
+    case 2: launch_pdl(bn_bwd_apply_kernel<2>, dim3(gb.grid), gb.block, 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z,
+             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows); break;
+    default: launch_pdl(bn_bwd_apply_kernel<4>, dim3(gb.grid), gb.block, 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z,
+             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows); break;
+  }
   return check_launch("ft3d_bn_bwd_apply");
 }
 

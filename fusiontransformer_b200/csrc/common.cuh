@@ -65,6 +65,7 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_trigger();
 }
 
+int row_batch();    // FT3D_ROWBATCH = 1 | 2 | 4: rows a thread of the streaming kernels keeps in flight (default 2, measured best on B200)
 bool pdl_enabled();   // FT3D_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops)
 
 template <typename... KArgs, typename... Args>

@@ -62,13 +62,41 @@ __device__ __forceinline__ bool pair_tile(const int32_t* off, int K, int item, i
   return false;
 }
 
+// Walks consecutive tiles of a pair list in O(1) per step (pair_tile() scans the K offsets: used once, to seek).
+struct TileCursor {
+  const int32_t* off;
+  int K, k, begin, end;
+  __device__ __forceinline__ void seek(const int32_t* off_, int K_, int item) {
+    off = off_;
+    K = K_;
+    if (!pair_tile(off, K, item, kTileRows, &k, &begin, &end)) k = K, begin = end = 0;
+  }
+  __device__ __forceinline__ void next() {
+    int nb = begin + kTileRows;
+    if (k < K && nb < off[k + 1]) {
+      begin = nb;
+      end = min(nb + kTileRows, off[k + 1]);
+      return;
+    }
+    do { ++k; } while (k < K && off[k + 1] <= off[k]);
+    if (k >= K) {
+      begin = end = 0;
+      return;
+    }
+    begin = off[k];
+    end = min(begin + kTileRows, off[k + 1]);
+  }
+};
+
 // gather one [128 x nchunk*16B] swizzled block of bf16 rows with cp.async (zero-fill for idx < 0)
 __device__ __forceinline__ void gather_block_bf16(uint8_t* block, const __nv_bfloat16* __restrict__ src, int row_width,
                                                   int col0, int nchunk, int tid, const int32_t* __restrict__ s_idx) {
   const uint32_t base = smem_u32(block);
   const int total = kTileRows * nchunk;
+  const int sh = 31 - __clz(nchunk);
+  const bool pow2 = (nchunk & (nchunk - 1)) == 0;          // 2, 4 or 8 chunks for every channel width of the network
   for (int q = tid; q < total; q += kPProducers) {
-    const int r = q / nchunk;
+    const int r = pow2 ? (q >> sh) : (q / nchunk);
     const int c = q - r * nchunk;
     const int g = s_idx[r];
     const __nv_bfloat16* p = src + (g >= 0 ? (int64_t)g * row_width + col0 + c * 8 : 0);
@@ -257,6 +285,8 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
     for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
   } else {
     T = (int)((n_identity + kTileRows - 1) / kTileRows);
+    if (tid == 0) hdr->off[0] = 0, hdr->off[1] = (int32_t)n_identity;     // identity gather = one offset of n rows
+    K = 1;
   }
   const int chunk = (T + (int)gridDim.x - 1) / (int)gridDim.x;
   const int g0 = (int)blockIdx.x * chunk;
@@ -286,22 +316,13 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
   pdl_enter();      // launch, schedule, barrier and TMEM set-up ran under the predecessor's tail
   const uint32_t tmem_base = hdr->tmem_base;
 
-  auto tile_of = [&](int g, int* k, int* begin, int* end) {
-    if (pairs != nullptr) {
-      pair_tile(hdr->off, K, g, kTileRows, k, begin, end);
-    } else {
-      *k = 0;
-      *begin = g * kTileRows;
-      *end = (int)min((int64_t)*begin + kTileRows, n_identity);
-    }
-  };
-
   if (warp < 4) {
     // ------------------------------------------------------------------ gather producers
     uint32_t cnt = 0;
-    for (int g = g0; g < g1; ++g) {
-      int k, begin, end;
-      tile_of(g, &k, &begin, &end);
+    TileCursor cur;
+    cur.seek(hdr->off, K, g0);
+    for (int g = g0; g < g1; ++g, cur.next()) {
+      const int begin = cur.begin, end = cur.end;
       const int p = begin + tid;
       int gi = -1;
       if (p < end) {
@@ -329,9 +350,10 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
     if (lane == 0) {
       int cur_k = -1;
       uint32_t nb = 0;
-      for (int g = g0; g < g1; ++g) {
-        int k, begin, end;
-        tile_of(g, &k, &begin, &end);
+      TileCursor cur;
+      cur.seek(hdr->off, K, g0);
+      for (int g = g0; g < g1; ++g, cur.next()) {
+        const int k = cur.k;
         if (k == cur_k) continue;
         if (nb > 0) mbar_wait(&hdr->b_free, (nb - 1) & 1);     // every MMA that read the previous B_k has completed
         mbar_arrive_expect_tx(&hdr->b_full, (uint32_t)(nkb * b_bytes));
@@ -348,8 +370,9 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
       const uint32_t idesc = umma_idesc_bf16(128, ncols, 0, 0);
       int cur_k = -1;
       uint32_t nb = 0, cnt = 0;
-      int k, begin, end;
-      tile_of(g0, &k, &begin, &end);
+      TileCursor cur;
+      cur.seek(hdr->off, K, g0);
+      int k = cur.k;
       for (int g = g0; g < g1; ++g) {
         const int it = g - g0, buf = it & 1;
         const uint32_t ub = (uint32_t)it >> 1;
@@ -376,9 +399,10 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
           umma_commit(&hdr->empty_a[slot]);
         }
         umma_commit(&hdr->acc_full[buf]);
-        int nk = k, nbeg, nend;
+        int nk = k;
         if (g + 1 < g1) {
-          tile_of(g + 1, &nk, &nbeg, &nend);
+          cur.next();
+          nk = cur.k;
           if (nk != k) umma_commit(&hdr->b_free);
         }
         k = nk;
@@ -388,9 +412,10 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
     // ------------------------------------------------------------------ epilogue (TMEM quadrant = warp % 4)
     const int q = warp & 3;
     float* st = staging + (size_t)(warp - 6) * kV3StageFloats;
-    for (int g = g0; g < g1; ++g) {
-      int k, begin, end;
-      tile_of(g, &k, &begin, &end);
+    TileCursor cur;
+    cur.seek(hdr->off, K, g0);
+    for (int g = g0; g < g1; ++g, cur.next()) {
+      const int begin = cur.begin, end = cur.end;
       const int it = g - g0, buf = it & 1;
       mbar_wait(&hdr->acc_full[buf], ((uint32_t)it >> 1) & 1);
       tc_fence_after();
@@ -429,7 +454,7 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
 // terminated by -1).  2-D block: threadIdx.x = 4 channels, threadIdx.y = row lane; each CTA owns a contiguous chunk
 // of rows.  With STATS the per-channel sum / sum of squares of the rows just written are folded per CTA and a tiny
 // second launch turns them into the BatchNorm statistics of this layer (bn_common.cuh): the activation is not re-read.
-template <bool STATS>
+template <bool STATS, int RB>
 __global__ void __launch_bounds__(kColThreads)
 conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos, int64_t n_rows, int kpad, int ncols,
                    int rows_per_cta, float* __restrict__ out, float* __restrict__ partials) {
@@ -440,24 +465,58 @@ conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos
   const int64_t row1 = row0 + rows_per_cta < n_rows ? row0 + rows_per_cta : n_rows;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   const int nq = kpad >> 2;
-  for (int64_t row = row0 + threadIdx.y; row < row1; row += blockDim.y) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int4* pr = reinterpret_cast<const int4*>(ppos + row * kpad);
-    for (int q = 0; q < nq; ++q) {
-      const int4 pp = __ldg(pr + q);
-      if (pp.x < 0) break;
-      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.x * ncols + ch)));
-      if (pp.y < 0) break;
-      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.y * ncols + ch)));
-      if (pp.z < 0) break;
-      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.z * ncols + ch)));
-      if (pp.w < 0) break;
-      add4(acc, __ldg(reinterpret_cast<const float4*>(P + (int64_t)pp.w * ncols + ch)));
+  // A thread walks its rows four at a time: the four position quads are requested together, then all sixteen
+  // candidate partial rows (absent slots re-read partial row 0 and are discarded), so that ~16 independent 16-byte
+  // loads are in flight per thread instead of a serial  position -> partial -> next row  chain.  The additions keep
+  // the ascending-offset order, so the result is bit-identical to the one-row-at-a-time loop.
+  const int64_t rstep = blockDim.y;
+  for (int64_t rbase = row0 + threadIdx.y; rbase < row1; rbase += RB * rstep) {
+    int4 pp[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t row = rbase + i * rstep;
+      pp[i] = row < row1 ? __ldg(reinterpret_cast<const int4*>(ppos + row * kpad)) : make_int4(-1, -1, -1, -1);
     }
-    *reinterpret_cast<float4*>(out + row * ncols + ch) = acc;
-    if (STATS) {
-      add4(s1, acc);
-      fma4(s2, acc, acc);
+    float4 v[RB][4];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      v[i][0] = __ldg(reinterpret_cast<const float4*>(P + (int64_t)max(pp[i].x, 0) * ncols + ch));
+      v[i][1] = __ldg(reinterpret_cast<const float4*>(P + (int64_t)max(pp[i].y, 0) * ncols + ch));
+      v[i][2] = __ldg(reinterpret_cast<const float4*>(P + (int64_t)max(pp[i].z, 0) * ncols + ch));
+      v[i][3] = __ldg(reinterpret_cast<const float4*>(P + (int64_t)max(pp[i].w, 0) * ncols + ch));
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int64_t row = rbase + i * rstep;
+      if (row >= row1) break;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pp[i].x >= 0) add4(acc, v[i][0]);
+      if (pp[i].y >= 0) add4(acc, v[i][1]);
+      if (pp[i].z >= 0) add4(acc, v[i][2]);
+      if (pp[i].w >= 0) {
+        add4(acc, v[i][3]);
+        const int4* pr = reinterpret_cast<const int4*>(ppos + row * kpad);
+        for (int q = 1; q < nq; ++q) {                     // rows with more than four pairs (deep levels)
+          const int4 p4 = __ldg(pr + q);
+          if (p4.x < 0) break;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)p4.x * ncols + ch));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)max(p4.y, 0) * ncols + ch));
+          const float4 a2 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)max(p4.z, 0) * ncols + ch));
+          const float4 a3 = __ldg(reinterpret_cast<const float4*>(P + (int64_t)max(p4.w, 0) * ncols + ch));
+          add4(acc, a0);
+          if (p4.y < 0) break;
+          add4(acc, a1);
+          if (p4.z < 0) break;
+          add4(acc, a2);
+          if (p4.w < 0) break;
+          add4(acc, a3);
+        }
+      }
+      *reinterpret_cast<float4*>(out + row * ncols + ch) = acc;
+      if (STATS) {
+        add4(s1, acc);
+        fma4(s2, acc, acc);
+      }
     }
   }
   if (STATS) col_publish(s1, s2, partials, ncols, s_stage);
@@ -688,6 +747,8 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
     for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
   } else {
     T = (int)((n_identity + kTileRows - 1) / kTileRows);
+    if (tid == 0) hdr->off[0] = 0, hdr->off[1] = (int32_t)n_identity;
+    K = 1;
   }
   const int MB = (cin + 127) / 128;
   const int U = T * MB;
@@ -717,23 +778,33 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
   pdl_enter();
   const uint32_t tmem_base = hdr->tmem_base;
 
-  auto unit_of = [&](int u, int* mb, int* k, int* begin, int* end) {
-    *mb = u / T;
-    const int t = u - *mb * T;
-    if (pairs != nullptr) {
-      pair_tile(hdr->off, K, t, kTileRows, k, begin, end);
-    } else {
-      *k = 0;
-      *begin = t * kTileRows;
-      *end = (int)min((int64_t)*begin + kTileRows, n_identity);
+  // unit u = (Cin block u / T, tile u % T); walked with an O(1) cursor
+  struct UnitCursor {
+    TileCursor c;
+    int mb, t, T;
+    __device__ __forceinline__ void seek(const int32_t* off_, int K_, int T_, int u) {
+      T = T_;
+      mb = u / T;
+      t = u - mb * T;
+      c.seek(off_, K_, t);
+    }
+    __device__ __forceinline__ void next() {
+      if (++t == T) {
+        t = 0;
+        ++mb;
+        c.seek(c.off, c.K, 0);
+      } else {
+        c.next();
+      }
     }
   };
 
   if (warp < 4) {
     // ------------------------------------------------------------------ gather producers
-    for (int u = u0; u < u1; ++u) {
-      int mb, k, begin, end;
-      unit_of(u, &mb, &k, &begin, &end);
+    UnitCursor uc;
+    uc.seek(hdr->off, K, T, u0);
+    for (int u = u0; u < u1; ++u, uc.next()) {
+      const int mb = uc.mb, begin = uc.c.begin, end = uc.c.end;
       const int p = begin + tid;
       int ia = -1, ib = -1;
       if (p < end) {
@@ -769,9 +840,10 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, cout, 1, 1);
       int group = -1, pk = -1, pmb = -1;
-      for (int u = u0; u < u1; ++u) {
-        int mb, k, begin, end;
-        unit_of(u, &mb, &k, &begin, &end);
+      UnitCursor uc;
+      uc.seek(hdr->off, K, T, u0);
+      for (int u = u0; u < u1; ++u, uc.next()) {
+        const int mb = uc.mb, k = uc.c.k;
         const bool fresh = (k != pk || mb != pmb);
         if (fresh) {
           if (group >= 0) umma_commit(&hdr->acc_full[group & 1]);     // previous group complete -> flush warps
@@ -803,9 +875,15 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
     const int q = warp & 3;
     float* st = staging + (size_t)(warp - 6) * kV3StageFloats;
     int group = -1, pk = -1, pmb = -1;
+    UnitCursor uc;
+    uc.seek(hdr->off, K, T, u0);
     for (int u = u0; u <= u1; ++u) {
-      int mb = -1, k = -1, begin, end;
-      if (u < u1) unit_of(u, &mb, &k, &begin, &end);
+      int mb = -1, k = -1;
+      if (u < u1) {
+        mb = uc.mb;
+        k = uc.c.k;
+        uc.next();
+      }
       if (k == pk && mb == pmb) continue;
       if (group >= 0) {                                    // group (pk, pmb) is complete
         const int buf = group & 1;
@@ -963,12 +1041,22 @@ static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_ro
     FT3D_REQUIRE(stat && workspace && ((uintptr_t)workspace & 15) == 0 &&
                      workspace_bytes >= col_workspace_bytes(ncols) && (running_mean == nullptr) == (running_var == nullptr),
                  "%s: statistics need stat and a workspace of ft3d_bn_workspace(ncols) bytes", what);
-    launch_pdl(conv_reduce_kernel<true>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
-                                                        (float*)workspace);
+    switch (row_batch()) {
+      case 1: launch_pdl(conv_reduce_kernel<true, 1>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
+                                                        (float*)workspace); break;
+      case 2: launch_pdl(conv_reduce_kernel<true, 2>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
+                                                        (float*)workspace); break;
+      default: launch_pdl(conv_reduce_kernel<true, 4>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
+                                                        (float*)workspace); break;
+    }
     launch_pdl(col_finalize_kernel<0>, dim3(ncols / 4), dim3(kColThreads), 0, s, (const float*)workspace, g.grid, ncols, n_rows, eps, momentum,
                                                              stat, running_mean, running_var, 0, valid_rows);
   } else {
-    launch_pdl(conv_reduce_kernel<false>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr);
+    switch (row_batch()) {
+      case 1: launch_pdl(conv_reduce_kernel<false, 1>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr); break;
+      case 2: launch_pdl(conv_reduce_kernel<false, 2>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr); break;
+      default: launch_pdl(conv_reduce_kernel<false, 4>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr); break;
+    }
   }
   return check_launch(what);
 }

@@ -15,6 +15,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int row_batch() {
+  static int rb = 0;
+  if (rb == 0) {
+    const char* e = getenv("FT3D_ROWBATCH");
+    rb = e ? atoi(e) : 2;
+    if (rb != 1 && rb != 4) rb = 2;
+  }
+  return rb;
+}
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
