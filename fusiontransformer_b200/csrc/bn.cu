@@ -242,6 +242,21 @@ int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float 
   return check_launch("ft3d_bn_stats");
 }
 
+int ft3d_col_sum(const float* x, int64_t n, int32_t channels, float* out, int32_t accumulate, void* workspace,
+                 size_t workspace_bytes, ft3d_stream_t stream) {
+  FT3D_REQUIRE(n > 0 && x && out && workspace && channels >= 4 && channels % 4 == 0 && channels <= 1024,
+               "ft3d_col_sum: bad arguments (channels=%d)", channels);
+  FT3D_REQUIRE(aligned16(x) && aligned16(workspace), "ft3d_col_sum: pointers must be 16-byte aligned");
+  FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_col_sum: workspace too small");
+  ColGrid g = col_grid(n, channels / 4);
+  launch_pdl(bn_stats_kernel<2>, dim3(g.grid), g.block, 0, (cudaStream_t)stream, x, n, channels, g.rows_per_cta,
+             (float*)workspace, (const int32_t*)nullptr);
+  launch_pdl(col_finalize_kernel<2>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream,
+             (const float*)workspace, g.grid, channels, n, 0.f, 0.f, out, (float*)nullptr, (float*)nullptr, accumulate,
+             (const int32_t*)nullptr);
+  return check_launch("ft3d_col_sum");
+}
+
 int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma, const float* beta,
                   const float* res, int32_t relu, float* z, void* z16, const int32_t* valid_rows,
                   ft3d_stream_t stream) {

@@ -83,6 +83,7 @@ __device__ __forceinline__ void col_publish(float4 s1, float4 s2, float* __restr
 //           unbiased for running_var); out0 = stat [2,C] = (mean, rstd).
 //   MODE 1: BatchNorm backward sums; out0 = red [2,C] = (sum g/n, sum g*xhat/n), out1 = dgamma, out2 = dbeta
 //           (`accumulate`: added to what out1/out2 hold -- gradients written straight into the optimizer's arena).
+//   MODE 2: plain column sums; out0 [C] = sum over rows (+ out0 when `accumulate`).
 template <int MODE>
 __global__ void __launch_bounds__(kColThreads)
 col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels, int64_t n, float eps, float momentum,
@@ -144,6 +145,8 @@ col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels
         out1[c] = (float)((1.0 - momentum) * (double)out1[c] + (double)momentum * mean);
         out2[c] = (float)((1.0 - momentum) * (double)out2[c] + (double)momentum * unbiased);
       }
+    } else if (MODE == 2) {
+      out0[c] = (float)s1 + (accumulate ? out0[c] : 0.f);
     } else {
       out0[c] = (float)(s1 / (double)n);
       out0[channels + c] = (float)(s2 / (double)n);

@@ -219,6 +219,75 @@ class _BNAct(torch.autograd.Function):
         return gy, dgamma, dbeta, None, None
 
 
+class _LinearBNAct(torch.autograd.Function):
+    """``relu?(batch_norm(x @ W^T + b))`` for the point-branch / fusion MLPs (models/spvcnn.py:164-180,
+    middle_fusion.py:18-22) as one autograd node.  Forward and dX are library GEMMs (cuBLAS, as SURVEY 8(a14) allows);
+    the weight gradient -- a [out,in] result reduced over ~50k points, a shape cuBLAS serves with a 70 us split-K
+    kernel -- runs on the tcgen05 wgrad kernel (bf16 operands, fp32 accumulation) in tensor-core mode, and the bias
+    gradient is a deterministic column sum; both go straight into the gradient arena when there is one."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, relu, bn):
+        training = bn.training or bn.running_mean is None
+        rm, rv = (bn.running_mean, bn.running_var) if (bn.training and bn.track_running_stats) else (None, None)
+        x = x.contiguous()
+        y = torch.addmm(bias, x, weight.t()) if bias is not None else x.matmul(weight.t())
+        if training:
+            stat = ops.bn_stats(y, bn.eps, bn.momentum, rm, rv)
+        else:
+            stat = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)]).contiguous()
+        z, _ = ops.bn_apply(y, stat, gamma, beta, None, relu, want_f32=True, want_bf16=False)
+        ctx.training, ctx.beta, ctx.bias = training, beta, bias
+        ctx.save_for_backward(x, weight, y, gamma, stat, z if relu else None)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, weight, y, gamma, stat, mask = ctx.saved_tensors
+        beta, bias = ctx.beta, ctx.bias
+        gz = gz.contiguous()
+        out_f, in_f = weight.shape
+        sink = getattr(weight, "_ft3d_sink", None)
+        if sink is not None and not (sink.owns(weight) and sink.owns(gamma) and sink.owns(beta)
+                                     and (bias is None or sink.owns(bias))):
+            sink = None
+        if sink is not None:
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat, gamma.grad, beta.grad)
+        else:
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat)
+        tc = (conv_engine.mode() == "tc" and out_f % 16 == 0 and out_f <= 512 and in_f % 32 == 0 and in_f <= 256
+              and ctx.needs_input_grad[1])
+        gy, gy16, _ = ops.bn_bwd_apply(gz, y, None, mask, stat, gamma, red if ctx.training else None,
+                                       want_f32=True, want_bf16=tc, want_res=False)
+        gx = gy.matmul(weight) if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1]:
+            if tc:       # gW[out,in] = gy^T x : the wgrad kernel with (a, b) = (gy, x) and an identity pair list
+                gw = ops.conv_wgrad_pairs_tc(gy16, ops.to_bf16(x), None, None, 1, 0, out_f, in_f, x.shape[0],
+                                             into=weight.grad.view(1, out_f, in_f) if sink is not None else None)
+                gw = None if sink is not None else gw.view(out_f, in_f)
+            elif sink is not None:
+                weight.grad.addmm_(gy.t(), x)
+            else:
+                gw = gy.t().matmul(x)
+        if bias is not None and ctx.needs_input_grad[2]:
+            gb = ops.col_sum(gy, into=bias.grad if sink is not None else None)
+            if sink is not None:
+                gb = None
+        if sink is not None:
+            for p in (weight, bias, gamma, beta):
+                if p is not None:
+                    sink.note(p)
+        return gx, gw, gb, dgamma, dbeta, None, None
+
+
+def linear_bn_act(x: torch.Tensor, lin, bn, relu: bool) -> torch.Tensor:
+    out = _LinearBNAct.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, relu, bn)
+    if bn.training and bn.track_running_stats:
+        bn._ft3d_pending_batches = getattr(bn, "_ft3d_pending_batches", 0) + 1
+    return out
+
+
 def bn_act(y: torch.Tensor, bn, relu: bool) -> torch.Tensor:
     out = _BNAct.apply(y, bn.weight, bn.bias, relu, bn)
     if bn.training and bn.track_running_stats:
@@ -270,6 +339,12 @@ def _sequential_forward(self, x):
         if (isinstance(x, SparseTensor) and i + 1 < n and _fusable(m, mods[i + 1]) and x.F.is_cuda):
             relu = i + 2 < n and type(mods[i + 2]) is spnn.ReLU
             x = conv_bn_act(x, m, mods[i + 1], relu)
+            i += 3 if relu else 2
+        elif (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+              and type(m) is nn.Linear and i + 1 < n and _bn1d_fusable(mods[i + 1])
+              and m.in_features % 4 == 0 and m.out_features % 4 == 0):
+            relu = i + 2 < n and type(mods[i + 2]) is nn.ReLU
+            x = linear_bn_act(x, m, mods[i + 1], relu)
             i += 3 if relu else 2
         elif (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
               and _bn1d_fusable(m)):

@@ -495,6 +495,15 @@ def bn_stats(y, eps, momentum, running_mean, running_var):
     return stat
 
 
+def col_sum(x, into=None):
+    """Column sums of an fp32 [N,C] tensor; with ``into`` they are ADDED to that tensor (gradient arena)."""
+    n, c = x.shape
+    out = into if into is not None else torch.empty((c,), dtype=torch.float32, device=x.device)
+    ws = bn_scratch(x.device)
+    lib().col_sum(x.data_ptr(), n, c, out.data_ptr(), int(into is not None), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
 def bn_apply(y, stat, gamma, beta, res, relu: bool, want_f32: bool = True, want_bf16: bool = True):
     n, c = y.shape
     z = torch.empty((n, c), dtype=torch.float32, device=y.device) if want_f32 else None

@@ -218,6 +218,10 @@ size_t ft3d_bn_workspace(int32_t channels);
 int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float momentum, float* stat,
                   float* running_mean, float* running_var, const int32_t* valid_rows, void* workspace,
                   size_t workspace_bytes, ft3d_stream_t stream);
+/* out[c] (+)= sum over rows of x[:, c]  (deterministic two-stage sum in double; bias gradient of the point-branch
+ * nn.Linear layers, models/spvcnn.py:164-180).  workspace: ft3d_bn_workspace(channels) bytes. */
+int ft3d_col_sum(const float* x, int64_t n, int32_t channels, float* out, int32_t accumulate, void* workspace,
+                 size_t workspace_bytes, ft3d_stream_t stream);
 /* z = [relu]((y - mean) * rstd * gamma + beta [+ res]); writes z f32 [n,C] (nullable) and z16 bf16 [n,C]
  * (nullable) -- the copy the next convolution gathers.  Evaluation mode: pass stat built from the running stats. */
 int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma,

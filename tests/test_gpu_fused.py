@@ -247,3 +247,46 @@ def test_multi_pack_equals_per_layer_pack(monkeypatch):
         ops._PACK_CACHE.clear()
         single = ops.packed_weights(w.contiguous(), wt)
         assert torch.equal(single, img), (tuple(p.shape), wt)
+
+
+@pytest.mark.parametrize("mode,tol", [("f32", 1e-4), ("tc", 5e-3)])
+@pytest.mark.parametrize("inc,outc,sink", [(32, 256, False), (256, 128, True), (96, 256, True), (128, 96, False)])
+def test_fused_point_mlp_matches_torch(monkeypatch, mode, tol, inc, outc, sink):
+    """Linear -> BatchNorm1d -> ReLU of the point branch (models/spvcnn.py:164-180) as one node: forward, input
+    gradient and all four parameter gradients (the weight gradient runs on the tcgen05 wgrad kernel in tc mode, the
+    bias gradient on the column-sum kernel) against the plain torch chain on the CPU in fp64."""
+    from fusiontransformer_b200 import spvcnn as sp
+    from fusiontransformer_b200.dp import GradSync
+    monkeypatch.setenv("FT3D_CONV", mode)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", mode == "tc")     # the library GEMMs' precision
+    torch.manual_seed(3)
+    ref = torch.nn.Sequential(torch.nn.Linear(inc, outc), torch.nn.BatchNorm1d(outc), torch.nn.ReLU(True)).double()
+    with torch.no_grad():
+        ref[1].weight.uniform_(0.5, 1.5)
+        ref[1].bias.uniform_(-0.5, 0.5)
+    mlp = sp._point_mlp(inc, outc)
+    mlp.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    from fusiontransformer_b200.fused import fuse
+    mlp = fuse(mlp).cuda().train()
+    assert getattr(mlp, "_ft3d_fused", False)
+    if sink:
+        GradSync(mlp)
+    n = 5000
+    x = torch.randn(n, inc, dtype=torch.float64)
+    w = torch.randn(n, outc, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    out_ref = ref(xr)                       # one training-mode forward: the running statistics move once
+    (out_ref * w).sum().backward()
+    xg = x.float().cuda().requires_grad_(True)
+    out = mlp(xg)
+    (out * w.float().cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(out, out_ref.detach()) < tol
+    assert rel_l2(xg.grad, xr.grad) < tol
+    for (name, po), (_, pg) in zip(ref.named_parameters(), mlp.named_parameters()):
+        # the Linear bias gradient is analytically zero (BatchNorm removes a per-channel shift): what is compared there
+        # is fp32 summation noise over n rows, so it is scaled by the size of the summed gradient instead
+        scale = max(po.grad.norm().item(), 1e-2 * w.norm().item())
+        err = (pg.grad.double().cpu() - po.grad).norm().item() / scale
+        assert err < tol, (name, err)
+    assert rel_l2(mlp[1].running_var, ref[1].running_var) < 1e-4
