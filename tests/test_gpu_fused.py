@@ -258,7 +258,9 @@ def test_fused_point_mlp_matches_torch(monkeypatch, mode, tol, inc, outc, sink):
     from fusiontransformer_b200 import spvcnn as sp
     from fusiontransformer_b200.dp import GradSync
     monkeypatch.setenv("FT3D_CONV", mode)
-    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", mode == "tc")     # the library GEMMs' precision
+    # library GEMMs in fp32 in both modes: what is under test are the libft3d kernels (tc mode: the bf16 tensor-core
+    # weight gradient).  TF32 forward rounding would flip ReLU masks the fp64 reference cannot reproduce.
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
     torch.manual_seed(3)
     ref = torch.nn.Sequential(torch.nn.Linear(inc, outc), torch.nn.BatchNorm1d(outc), torch.nn.ReLU(True)).double()
     with torch.no_grad():
@@ -281,12 +283,13 @@ def test_fused_point_mlp_matches_torch(monkeypatch, mode, tol, inc, outc, sink):
     out = mlp(xg)
     (out * w.float().cuda()).sum().backward()
     torch.cuda.synchronize()
-    assert rel_l2(out, out_ref.detach()) < tol
-    assert rel_l2(xg.grad, xr.grad) < tol
+    assert rel_l2(out, out_ref.detach()) < 1e-4
+    gtol = max(tol, 1e-3)           # a few of the n*outc ReLU masks flip under fp32 rounding of the pre-activation
+    assert rel_l2(xg.grad, xr.grad) < gtol
     for (name, po), (_, pg) in zip(ref.named_parameters(), mlp.named_parameters()):
         # the Linear bias gradient is analytically zero (BatchNorm removes a per-channel shift): what is compared there
         # is fp32 summation noise over n rows, so it is scaled by the size of the summed gradient instead
         scale = max(po.grad.norm().item(), 1e-2 * w.norm().item())
         err = (pg.grad.double().cpu() - po.grad).norm().item() / scale
-        assert err < tol, (name, err)
+        assert err < gtol, (name, err)
     assert rel_l2(mlp[1].running_var, ref[1].running_var) < 1e-4
