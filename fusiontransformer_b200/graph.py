@@ -59,13 +59,16 @@ class _Slot:
 class StaticGeometry:
     """Capacity-padded, fixed-address image of (GeometryPlan + the batch's voxelized inputs)."""
 
-    def __init__(self, plan: GeometryPlan, slack: float = 1.10, granule: int = 128):
+    def __init__(self, plan: GeometryPlan, slack: float = 1.10, granule: int = 128, prev: "StaticGeometry" = None):
+        """``prev``: the geometry this one replaces -- no capacity shrinks below its value, so a stream of batches whose
+        sizes wander (one larger in points, the next larger at stride 8 ...) converges after a few re-captures instead
+        of re-capturing for ever."""
         dev = plan.point_coords.device
         self.device = dev
         used_caps = set()
 
-        def cap_rows(n):
-            c = _round_up(int(n * slack) + 1, granule)
+        def cap_rows(n, floor=0):
+            c = _round_up(max(int(n * slack) + 1, floor), granule)
             while c in used_caps:                       # row capacities double as keys of ops.ROW_COUNTS
                 c += granule
             used_caps.add(c)
@@ -75,8 +78,9 @@ class StaticGeometry:
         self.full_tables = conv_engine.mode() == "f32"   # exact-precision mode gathers through nbr / nbrT everywhere
         ex = plan.extras
         self.strides = sorted(plan.coord_maps)
-        self.n_points_cap = cap_rows(plan.point_coords.shape[0])
-        self.row_caps = {s: cap_rows(plan.coord_maps[s].shape[0]) for s in self.strides}
+        self.n_points_cap = cap_rows(plan.point_coords.shape[0], prev.n_points_cap if prev is not None else 0)
+        self.row_caps = {s: cap_rows(plan.coord_maps[s].shape[0],
+                                     prev.row_caps.get(s, 0) if prev is not None else 0) for s in self.strides}
         self.slots = {}
 
         def slot(name, cap, tail, dtype, pad):
@@ -97,7 +101,8 @@ class StaticGeometry:
         for key, km in plan.kernel_maps.items():
             s_in, s_out = self._map_strides(key)
             kpad = km.nbr.shape[1]
-            lcap = _round_up(int(km.num_pairs() * slack) + 1, 128)
+            lcap = _round_up(max(int(km.num_pairs() * slack) + 1,
+                                 prev.pair_caps.get(key, 0) if prev is not None else 0), 128)
             self.pair_caps[key] = lcap
             want_nbr = self.full_tables or key == self._stem_key()
             nbr = slot(key + ".nbr", self.row_caps[s_out], (kpad,), torch.int32, -1) if want_nbr else None
@@ -225,7 +230,13 @@ class GraphedStep:
     def _capture(self, plan: GeometryPlan):
         from . import _lib
         self.graph = None                                   # release the previous private pool first
-        self.static = StaticGeometry(plan, self.slack)
+        prev = None
+        if self.static is not None:                          # keep only the numbers: the old buffers are freed first
+            import types
+            prev = types.SimpleNamespace(n_points_cap=self.static.n_points_cap, row_caps=dict(self.static.row_caps),
+                                         pair_caps=dict(self.static.pair_caps))
+        self.static = None
+        self.static = StaticGeometry(plan, self.slack, prev=prev)
         self.static.load(plan)
         splan = self.static.as_plan()
         prev_counts = ops.ROW_COUNTS
