@@ -108,6 +108,10 @@ class GradSync:
         self._join_side()
         if self.world == 1:
             return
+        if self.deferred:
+            # nothing was launched from hooks, and under CUDA-graph replay zero_grad() (which re-arms the buckets) runs
+            # only inside the captured graph, not in Python: every bucket is exchanged here, every step
+            self._launched = [False] * len(self.buckets)
         for b in range(len(self.buckets)):
             self._launch(b)
         if self.overlap:

@@ -84,6 +84,49 @@ def test_gradsync_world2_matches_full_batch():
         assert torch.allclose(got, want, atol=1e-6)
 
 
+def _worker_deferred(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fusiontransformer_b200.dp import GradSync
+    torch.manual_seed(7)
+    net = Net()
+    sync = GradSync(net, bucket_bytes=256)
+    sync.deferred = True                       # CUDA-graph mode: hooks launch nothing, finish() exchanges everything
+    out = []
+    for step in range(3):
+        if step == 0:
+            sync.zero_grad()                   # the capture step runs the Python body once ...
+        else:
+            sync.flat.zero_()                  # ... a replay only re-executes the captured memset: no Python zero_grad
+        g = torch.Generator().manual_seed(10 * step + rank)
+        x = torch.randn(4, 8, generator=g)
+        net(x).sum().backward()
+        assert sum(sync._launched) == 0 or step > 0
+        sync.finish()
+        out.append(sync.flat.clone().numpy())
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_deferred_exchange_runs_on_every_step_without_python_zero_grad():
+    """Regression: under graph replay zero_grad() is not executed in Python, so finish() must re-arm the buckets
+    itself -- otherwise only capture steps exchange gradients and ranks that re-capture deadlock the others."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_deferred, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(3):
+        a, b = torch.from_numpy(res[0][step]), torch.from_numpy(res[1][step])
+        assert torch.allclose(a, b) and a.abs().sum() > 0        # averaged over ranks on every step, not only the first
+
+
 def test_shard_indices_wraps_like_distributed_sampler():
     from fusiontransformer_b200.dp import shard_indices
     assert shard_indices(5, 0, 2) == [0, 2, 4] and shard_indices(5, 1, 2) == [1, 3, 0]
