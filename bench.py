@@ -200,7 +200,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         # a mismatched collective must fail in minutes, not hold the box for NCCL's 10-minute default
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("FT3D_NCCL_TIMEOUT_S", "180"))))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
     wl = WORKLOADS[args.workload]

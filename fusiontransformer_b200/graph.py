@@ -256,7 +256,8 @@ class GraphedStep:
             ops.FORCE_REPACK = True                         # weight images must be re-packed inside every replay
             ops.PACK_EPOCH += 1
             try:
-                with torch.cuda.graph(g, stream=self.stream):
+                with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):   # NCCL's watchdog
+                    # thread polls events while we capture; only this thread's calls must be capture-safe
                     self.loss = self.body(splan)
             finally:
                 ops.FORCE_REPACK = False
