@@ -237,6 +237,7 @@ def main():
         return time.perf_counter()
 
     from fusiontransformer_b200.fused import weight_packer
+    from fusiontransformer_b200.losses import seg_loss
     packer = weight_packer(net) if conv_engine.mode() == "tc" else None
 
     def fwd_bwd(plan):
@@ -245,7 +246,7 @@ def main():
         ex = plan.extras
         img = ft.nn.functional.lift(fmap, ex["rc"], ex["bidx"]) if args.fusion != "none" else None
         out = net(ex["lidar"], None if img is None else img.detach(), plan=plan)
-        loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], ex["labels"])
+        loss = seg_loss(out["lidar_seg_logit"], ex["labels"])      # CE forward + gradient in one libft3d pass
         sync.zero_grad()
         loss.backward()
         return loss

@@ -118,7 +118,7 @@ LAUNCHES = {
     "v2p_build": 1, "p2v_build": 2, "lift_fwd": 1, "lift_bwd": 1, "conv_gather_f32": 1, "conv_wgrad_f32": 1,
     "conv_pack_weights": 1, "conv_gather_tc": 1, "conv_wgrad_tc": 1, "to_bf16": 1, "conv_pairs_tc": 1,
     "conv_reduce": 1, "conv_wgrad_pairs_tc": 1, "kmap_pair_positions": 3, "conv_reduce_bn": 2, "bn_stats": 2,
-    "bn_apply": 1, "col_sum": 2, "bn_bwd_reduce": 2, "conv_pack_weights_multi": 1, "bn_bwd_apply": 1,
+    "bn_apply": 1, "col_sum": 2, "seg_loss": 3, "confusion_update": 1, "bn_bwd_reduce": 2, "conv_pack_weights_multi": 1, "bn_bwd_apply": 1,
 }
 
 

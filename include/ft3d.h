@@ -240,6 +240,23 @@ int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const fl
                       int32_t channels, const float* stat, const float* gamma, const float* red, float* gy,
                       void* gy16, float* gres, const int32_t* valid_rows, ft3d_stream_t stream);
 
+/* ---- segmentation loss and metric on the device ----------------------------------------------
+ * ft3d_seg_loss: modules/SemanticTorchpackTrainer.py:70-108.  loss = (1-l) * CE + l * KL with
+ *   CE = F.cross_entropy(logits, labels, weight=class_weight, ignore_index)   (weighted mean over live rows)
+ *   KL = F.kl_div(log_softmax(logits), softmax(teacher), 'none').sum(1).mean()   (teacher = the other modality's
+ *        detached logits; nullable with lambda_xm == 0)
+ * and its gradient with respect to the logits, in one pass.  logits/teacher/grad_out f32 [n, C] (C <= 64), labels
+ * int64 [n], loss_out f32 [4] = {loss, CE, KL, sum of weights}.  valid_rows (nullable): device int32 holding the
+ * real row count when n is a padded capacity.  workspace: ft3d_seg_loss_workspace() bytes, 8-byte aligned.
+ * ft3d_confusion_update: models/metric.py:37-58 (SegIoU.update_dict): mat[label, argmax(logits)] += 1 for
+ * labels != ignore_index; mat int64 [C, C], accumulated in place. */
+size_t ft3d_seg_loss_workspace(void);
+int ft3d_seg_loss(const float* logits, const int64_t* labels, int64_t n, int32_t num_classes, int64_t ignore_index,
+                  const float* class_weight, const float* teacher_logits, float lambda_xm, const int32_t* valid_rows,
+                  float* loss_out, float* grad_out, void* workspace, size_t workspace_bytes, ft3d_stream_t stream);
+int ft3d_confusion_update(const float* logits, const int64_t* labels, int64_t n, int32_t num_classes,
+                          int64_t ignore_index, const int32_t* valid_rows, int64_t* mat, ft3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
