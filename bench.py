@@ -495,7 +495,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sps, spstep, done = time_oracle(wl["shape"], steps=3, warmup=1, budget_s=30.0)
+        sps, spstep, done = time_oracle(wl["shape"], steps=24, warmup=1, budget_s=15.0)
         cpu_baseline = {"value": sps, "unit": "scans/s", "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": "%d single-scan train steps (fwd+bwd+Adam) of the CPU oracle after 1 warm-up, %.1f s/step"
                                   % (done, spstep)}
