@@ -254,11 +254,16 @@ def main():
     # The compute of a step (lift, forward, loss, backward, optimizer) is captured once per capacity set as ONE CUDA
     # graph and replayed on capacity-padded geometry (fusiontransformer_b200/graph.py).  With N > 1 the NCCL gradient
     # exchange and the optimizer run eagerly after the replay.
-    gstep = None
+    gstep, in_graph = None, False
     if use_graph:
         from fusiontransformer_b200.fused import join_side_streams
         from fusiontransformer_b200.graph import GraphedStep
-        if world == 1:
+        # N > 1: the NCCL all-reduces are captured too (FT3D_DP_EXCHANGE=graph, default): each bucket is launched on the
+        # communication stream from the gradient hooks as soon as its last wgrad has landed, overlapping the rest of the
+        # backward chain, and the optimizer step stays inside the graph.  FT3D_DP_EXCHANGE=eager exchanges after the
+        # replay instead (one exposed 87 MB all-reduce + an eager optimizer step per step).
+        in_graph = world == 1 or os.environ.get("FT3D_DP_EXCHANGE", "graph") == "graph"
+        if in_graph:
             def body(plan):
                 loss = fwd_bwd(plan)
                 sync.finish()
@@ -510,7 +515,9 @@ def main():
                        "image_hw": [H, W], "parallelism": "dp%d" % world, "optimizer": "Adam(lr 1e-4, wd 5e-4)",
                        "geometry_prefetch": bool(args.prefetch) and not args.reuse_plans,
                        **({"INVALID_diagnostic": "geometry cached across steps"} if args.reuse_plans else {}),
-                       "cuda_graph": ("whole step, %d capture(s)" % gstep.captures) if gstep is not None else "off",
+                       "cuda_graph": ("whole step%s, %d capture(s)" % (
+                           "" if world == 1 else (" incl. NCCL exchange" if in_graph else ", exchange after replay"),
+                           gstep.captures)) if gstep is not None else "off",
                        "linear_layers": "cuBLAS TF32" if conv_engine.mode() == "tc" else "cuBLAS fp32",
                        "l2": "no explicit flush: %d distinct batches are cycled and the step's working set (348 MB of "
                              "weights+Adam state, the activations and the %.1f GB feature map) exceeds the 126 MB L2"
@@ -524,6 +531,14 @@ def main():
     if pre is not None:
         pre.close()
     if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if gstep is not None and in_graph:
+            # NCCL work captured in CUDA graphs: ProcessGroupNCCL's teardown waited for ever on this stack (torch 2.11,
+            # NCCL 2.28) although every collective had completed (the timings above were exchanged and read).  All
+            # results are out; leave without the teardown.
+            os._exit(0)
         dist.barrier()
         dist.destroy_process_group()
 
