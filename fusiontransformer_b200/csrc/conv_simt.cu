@@ -19,6 +19,40 @@ conv_gather_f32_kernel(const float* __restrict__ in, const int32_t* __restrict__
   float acc[kMaxColsPerLane];
   #pragma unroll
   for (int t = 0; t < kMaxColsPerLane; ++t) acc[t] = 0.f;
+  if (red == 4 && K <= 32 && (((uintptr_t)in) & 15) == 0) {
+    // 4-channel input (the stem convolution, models/spvcnn.py:87-93): lane k fetches neighbour k's index and then its
+    // whole 16-byte feature row, so the warp makes two dependent round trips in total instead of one per offset; the
+    // offsets are then walked in ascending order through shuffles (same summation order as the general loop below).
+    const int src = lane < K ? __ldg(nbr + row * kpad + lane) : -1;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src >= 0) a4 = __ldg(reinterpret_cast<const float4*>(in + (int64_t)src * 4));
+    unsigned mask = __ballot_sync(0xffffffffu, src >= 0);
+    while (mask) {
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float av[4] = {__shfl_sync(0xffffffffu, a4.x, k), __shfl_sync(0xffffffffu, a4.y, k),
+                           __shfl_sync(0xffffffffu, a4.z, k), __shfl_sync(0xffffffffu, a4.w, k)};
+      const int kw = kflip ? (K - 1 - k) : k;
+      const float* wk = w + (int64_t)kw * 4 * ncols;
+      #pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        #pragma unroll
+        for (int t = 0; t < kMaxColsPerLane; ++t) {
+          const int c = lane + 32 * t;
+          if (c < ncols) {
+            const float bv = w_transposed ? __ldg(wk + (int64_t)c * 4 + r) : __ldg(wk + (int64_t)r * ncols + c);
+            acc[t] = fmaf(av[r], bv, acc[t]);
+          }
+        }
+      }
+    }
+    #pragma unroll
+    for (int t = 0; t < kMaxColsPerLane; ++t) {
+      const int c = lane + 32 * t;
+      if (c < ncols) out[row * ncols + c] = acc[t];
+    }
+    return;
+  }
   for (int k = 0; k < K; ++k) {
     int src = __ldg(nbr + row * kpad + k);
     if (src < 0) continue;
