@@ -70,7 +70,6 @@ bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_p
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
   const float4 m = ld4(stat + ch), rs = ld4(stat + channels + ch), g = ld4(gamma + ch), b = ld4(beta + ch);
-  const float4 sc = make_float4(rs.x * g.x, rs.y * g.y, rs.z * g.z, rs.w * g.w);
   const int64_t rstep = blockDim.y;
   for (int64_t r = row0 + threadIdx.y; r < row1; r += RB * rstep) {
     float4 v[RB], rr[RB];
@@ -101,7 +100,6 @@ bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_p
         *reinterpret_cast<uint2*>(z16 + row * channels + ch) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
   }
-  (void)sc;
 }
 
 // ------------------------------------------------------------------------------------------------ backward
