@@ -1,6 +1,8 @@
 """SURVEY 8(f) "next" rows: lift straight from the low-resolution image-feature map (rank 2), loss and IoU metric
 on the device (rank 4).  Oracles are the reference's own expressions in plain torch (they are executable here:
 image_models_billinear.py:8-23,117-124; SemanticTorchpackTrainer.py:70-108; metric.py:37-58)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -124,3 +126,37 @@ def test_seg_iou_matches_reference_metric():
     iou = torch.diag(h) / (h.sum(1) + h.sum(0) - torch.diag(h))
     assert torch.allclose(m.iou.cpu(), iou, equal_nan=True)
     assert abs(m.global_avg - iou.mean().item()) < 1e-6 or (np.isnan(m.global_avg) and torch.isnan(iou.mean()))
+
+
+# ------------------------------------------------------------------ vectors produced by the reference's own code
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["nus", "kitti"])
+def test_device_voxelization_matches_reference_augment_and_scale(tag):
+    """a1 on the GPU (ft3d_scale_coords) against augmentation_3d.py + dataloader :220,:225 run by the reference."""
+    import fusiontransformer_b200 as ft
+    g = np.load(os.path.join(GOLD, "ref_voxelize.npz"))
+    pts = torch.from_numpy(g[tag + "_points"]).cuda()
+    sid = torch.zeros(len(pts), dtype=torch.int32, device="cuda")
+    vc, kept, inds, inv, counts = ft.utils.sparse_quantize_batch(pts, sid, 1)
+    keep = g[tag + "_keep"]
+    np.testing.assert_array_equal(kept.cpu().numpy(), np.nonzero(keep)[0])
+    np.testing.assert_array_equal(vc[:, :3].cpu().numpy(), g[tag + "_coords"][keep])
+    np.testing.assert_array_equal(vc[inds.long()][inv.long()][:, :3].cpu().numpy(), g[tag + "_coords"][keep])
+
+
+@pytest.mark.gpu
+def test_device_seg_iou_matches_reference_metric_fixture():
+    """(f)4: losses.SegIoU against FusionTransformer/models/metric.py:SegIoU run by the reference on the same data."""
+    from fusiontransformer_b200.losses import SegIoU
+    g = np.load(os.path.join(GOLD, "ref_segiou.npz"))
+    m = SegIoU(20, ignore_index=0, name="seg_iou_3d")
+    for step in range(2):
+        m.update_dict({"lidar_seg_logit": torch.from_numpy(g["logits%d" % step]).cuda()},
+                      {"seg_label": torch.from_numpy(g["labels%d" % step]).cuda()})
+    np.testing.assert_array_equal(m.mat.cpu().numpy(), g["mat"])
+    np.testing.assert_allclose(m.iou.cpu().numpy(), g["iou"], rtol=1e-6, equal_nan=True)
+    pred = torch.from_numpy(g["logits1"]).cuda().argmax(1)
+    np.testing.assert_array_equal(pred[torch.from_numpy(g["inverse_map"]).cuda()].cpu().numpy(), g["pred_points"])

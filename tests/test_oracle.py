@@ -222,3 +222,24 @@ def test_golden_fixtures(name):
             np.testing.assert_allclose(got[k], want[k], rtol=2e-4, atol=2e-5, err_msg=k)
         else:
             np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+
+
+# ---- vectors produced by the reference's own code (tests/golden/make_reference_golden.py) -------------------------
+@pytest.mark.parametrize("tag", ["nus", "kitti"])
+def test_oracle_voxelize_matches_reference_augment_and_scale(tag):
+    """a1: the oracle's restatement against FusionTransformer/data/utils/augmentation_3d.py run on the same points."""
+    from oracle import ft_glue as og
+    g = np.load(os.path.join(GOLD, "ref_voxelize.npz"))
+    vc, keep, inds, inv = og.voxelize_scan(g[tag + "_points"])
+    np.testing.assert_array_equal(keep, g[tag + "_keep"])
+    np.testing.assert_array_equal(vc, g[tag + "_coords"][g[tag + "_keep"]])
+    if tag == "kitti":
+        assert 0 < keep.sum() < len(keep)                 # the bounds filter is exercised
+    np.testing.assert_array_equal(vc[inds][inv], vc)      # a2 round trip on the reference's coordinates
+
+
+def test_oracle_unmap_matches_reference_map_sparse_to_org():
+    from oracle import ft_glue as og
+    g = np.load(os.path.join(GOLD, "ref_segiou.npz"))
+    pred = torch.from_numpy(g["logits1"]).argmax(1)
+    np.testing.assert_array_equal(og.map_sparse_to_org(pred, torch.from_numpy(g["inverse_map"])).numpy(), g["pred_points"])
