@@ -4,6 +4,8 @@ and can be executed in the build container:   python -m tests.golden.make_refere
   * a1  FusionTransformer/data/utils/augmentation_3d.py:4-53 `augment_and_scale_3d` (numpy only), followed by the two
         dataloader lines that turn its output into voxel coordinates (semantic_kitti_dataloader.py:220 cast, :225
         bounds mask -- inside a Dataset.__getitem__ that needs the KITTI files, so they are restated literally here);
+  * a3  FusionTransformer/data/collate.py:6-86 `collate_scn_base` (its SparseTensor import resolves to this package's
+        container through install_as_torchsparse());
   * a16 FusionTransformer/data/utils/validate.py:10-11 `map_sparse_to_org`;
   * (f)4 FusionTransformer/models/metric.py:26-82 `SegIoU` (update_dict / iou), torch only.
 
@@ -58,12 +60,36 @@ def gen_ref_segiou():
     return out
 
 
+def gen_ref_collate():
+    """a3: FusionTransformer/data/collate.py:6-86 `collate_scn_base`, imported from the reference tree.  Its one
+    dependency, torchsparse's SparseTensor container, is provided by this package's alias (a plain holder of .C/.F)."""
+    sys.path.insert(0, REF)
+    import fusiontransformer_b200 as ft
+    ft.install_as_torchsparse()
+    from FusionTransformer.data.collate import collate_scn_base
+    from fusiontransformer_b200.synthetic import make_scan
+    from oracle import ft_glue as og
+    dicts, out = [], {}
+    for i in range(3):
+        s = make_scan("nuscenes", 20 + i)
+        vc, keep, inds, inv = og.voxelize_scan(s["points"])
+        d = dict(voxel_coords=vc, coords=vc[inds], feats=s["feats"][keep][inds], seg_label=s["seg_labels"][keep][inds],
+                 img=np.zeros((3, 4, 4), np.float32), img_indices=s["points_img"][keep][inds], seq="00", filename="%06d" % i)
+        dicts.append(d)
+        out["coords%d" % i], out["feats%d" % i], out["labels%d" % i] = d["coords"], d["feats"], d["seg_label"]
+    batch = collate_scn_base(dicts, output_orig=False)
+    out["C"], out["F"], out["seg_label"] = batch["lidar"].C.numpy(), batch["lidar"].F.numpy(), batch["seg_label"].numpy()
+    assert isinstance(batch["img_indices"], list) and len(batch["img_indices"]) == 3
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("the reference tree is needed to regenerate these fixtures")
     np.savez_compressed(os.path.join(HERE, "ref_voxelize.npz"), **gen_ref_voxelize())
     np.savez_compressed(os.path.join(HERE, "ref_segiou.npz"), **gen_ref_segiou())
-    for f in ("ref_voxelize.npz", "ref_segiou.npz"):
+    np.savez_compressed(os.path.join(HERE, "ref_collate.npz"), **gen_ref_collate())
+    for f in ("ref_voxelize.npz", "ref_segiou.npz", "ref_collate.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

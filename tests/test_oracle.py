@@ -243,3 +243,13 @@ def test_oracle_unmap_matches_reference_map_sparse_to_org():
     g = np.load(os.path.join(GOLD, "ref_segiou.npz"))
     pred = torch.from_numpy(g["logits1"]).argmax(1)
     np.testing.assert_array_equal(og.map_sparse_to_org(pred, torch.from_numpy(g["inverse_map"])).numpy(), g["pred_points"])
+
+
+def test_oracle_collate_matches_reference_collate_scn_base():
+    """a3: batch-index column, concatenation order and dtypes of FusionTransformer/data/collate.py:36-67."""
+    from oracle import ft_glue as og
+    g = np.load(os.path.join(GOLD, "ref_collate.npz"))
+    st = og.collate([dict(coords=g["coords%d" % i], feats=g["feats%d" % i]) for i in range(3)])
+    assert st.C.dtype == torch.int64 and tuple(st.C.shape) == tuple(g["C"].shape)
+    np.testing.assert_array_equal(st.C.numpy(), g["C"])
+    np.testing.assert_array_equal(st.F.numpy(), g["F"])
