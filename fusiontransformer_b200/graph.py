@@ -56,6 +56,19 @@ class _Slot:
         self.used = n
 
 
+def capacity(n: int, slack: float, granule: int, floor: int = 0, taken: set | None = None) -> int:
+    """Row capacity for ``n`` real rows: ``slack`` head-room, rounded up to ``granule``, never below ``floor`` (the
+    capacity of the geometry being replaced: capacities only grow, so a stream of batches whose sizes wander converges
+    instead of re-capturing for ever), and distinct from every value in ``taken`` (capacities double as the keys of
+    ops.ROW_COUNTS, which maps a padded row count to the device scalar holding the real one)."""
+    c = _round_up(max(int(n * slack) + 1, floor), granule)
+    if taken is not None:
+        while c in taken:
+            c += granule
+        taken.add(c)
+    return c
+
+
 class StaticGeometry:
     """Capacity-padded, fixed-address image of (GeometryPlan + the batch's voxelized inputs)."""
 
@@ -68,11 +81,7 @@ class StaticGeometry:
         used_caps = set()
 
         def cap_rows(n, floor=0):
-            c = _round_up(max(int(n * slack) + 1, floor), granule)
-            while c in used_caps:                       # row capacities double as keys of ops.ROW_COUNTS
-                c += granule
-            used_caps.add(c)
-            return c
+            return capacity(n, slack, granule, floor, used_caps)
 
         from . import conv_engine
         self.full_tables = conv_engine.mode() == "f32"   # exact-precision mode gathers through nbr / nbrT everywhere

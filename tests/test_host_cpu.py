@@ -63,3 +63,23 @@ def test_conv3d_parameter_layout():
     assert spnn.Conv3d(32, 64, 1).kernel.shape == (32, 64)
     c = spnn.Conv3d(16, 8, 3)
     assert c.kernel.abs().max() <= 1.0 / (16 * 27) ** 0.5 + 1e-7
+
+
+def test_graph_capacities_only_grow_and_stay_distinct():
+    """graph.capacity: head-room, granule, monotone across re-captures (the KITTI-shaped batches used to re-capture on
+    most steps because a capacity could shrink), unique keys for ops.ROW_COUNTS."""
+    from fusiontransformer_b200.graph import capacity
+    assert capacity(1000, 1.10, 128) == 1152 and capacity(1000, 1.10, 128) % 128 == 0
+    assert capacity(900, 1.10, 128, floor=1152) == 1152            # a smaller batch does not shrink the buffers
+    assert capacity(2000, 1.10, 128, floor=1152) == 2304
+    taken = set()
+    caps = [capacity(n, 1.10, 128, 0, taken) for n in (1000, 1001, 1002, 5000)]
+    assert len(set(caps)) == 4 and caps[:3] == [1152, 1280, 1408]
+    # a wandering stream converges: after each size has been seen once nothing grows any more
+    sizes = [(50000, 20000), (47000, 22000), (52000, 19000), (49000, 21500)] * 3
+    caps, grows = (0, 0), 0
+    for a, b in sizes:
+        if a > caps[0] or b > caps[1]:                             # StaticGeometry.fits
+            caps = (capacity(a, 1.10, 128, caps[0]), capacity(b, 1.10, 128, caps[1]))
+            grows += 1
+    assert grows <= 2

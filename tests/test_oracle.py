@@ -253,3 +253,81 @@ def test_oracle_collate_matches_reference_collate_scn_base():
     assert st.C.dtype == torch.int64 and tuple(st.C.shape) == tuple(g["C"].shape)
     np.testing.assert_array_equal(st.C.numpy(), g["C"])
     np.testing.assert_array_equal(st.F.numpy(), g["F"])
+
+
+# ---- random occupancy: the sparse convolutions equal dense conv3d on the zero-filled grid, read at the active sites
+def _random_voxels(D, frac, C, seed, batch=2):
+    g = torch.Generator().manual_seed(seed)
+    occ = torch.rand(batch, D, D, D, generator=g) < frac
+    b, x, y, z = torch.nonzero(occ, as_tuple=True)
+    perm = torch.randperm(b.numel(), generator=g)                     # arbitrary input order, as after a dataloader
+    coords = torch.stack([x, y, z, b], 1)[perm].int()
+    feats = torch.randn(coords.shape[0], C, generator=g)
+    return coords, feats
+
+
+@pytest.mark.parametrize("seed,frac", [(0, 0.08), (1, 0.3), (2, 0.7)])
+def test_sparse_conv_k3_random_occupancy_matches_dense(seed, frac):
+    D, Cin, Cout = 9, 3, 5
+    coords, feats = _random_voxels(D, frac, Cin, seed)
+    w = torch.randn(27, Cin, Cout, generator=torch.Generator().manual_seed(seed + 10))
+    y = ts.conv3d(ts.SparseTensor(feats, coords, 1), w, 3)
+    assert torch.equal(y.C, coords)                                   # submanifold: outputs = inputs, same order
+    wd = w.view(3, 3, 3, Cin, Cout).permute(4, 3, 2, 1, 0).contiguous()
+    ref = F.conv3d(_dense(coords, feats, D, 2), wd, padding=1)
+    c = coords.long()
+    assert torch.allclose(y.F, ref[c[:, 3], :, c[:, 0], c[:, 1], c[:, 2]], atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("seed,frac", [(3, 0.1), (4, 0.5)])
+def test_strided_and_transposed_conv_random_occupancy_match_dense(seed, frac):
+    D, Cin, Cmid = 8, 4, 6
+    coords, feats = _random_voxels(D, frac, Cin, seed, batch=1)
+    g = torch.Generator().manual_seed(seed + 20)
+    w = torch.randn(8, Cin, Cmid, generator=g)
+    x = ts.SparseTensor(feats, coords, 1)
+    x.check()                                                         # registers coord_maps[1] (models/utils.py:31)
+    y = ts.conv3d(x, w, 2, stride=2)
+    # coarse sites = unique parents of the active fine voxels, in ascending hash order
+    parents = torch.unique((coords[:, :3].long() // 2) * 2, dim=0)
+    assert y.C.shape[0] == parents.shape[0]
+    h = ts.sphash(y.C)
+    assert torch.all(h[1:] > h[:-1])
+    wd = w.view(2, 2, 2, Cin, Cmid).permute(4, 3, 0, 1, 2).contiguous()
+    ref = F.conv3d(_dense(coords, feats, D), wd, stride=2)
+    c = y.C.long() // 2
+    assert torch.allclose(y.F, ref[0][:, c[:, 0], c[:, 1], c[:, 2]].t(), atol=1e-4, rtol=1e-4)
+    # transposed conv writes only at the ORIGINAL fine sites (cached encoder coordinates), values = dense transposed conv
+    wt = torch.randn(8, Cmid, 3, generator=g)
+    z = ts.conv3d(y, wt, 2, stride=2, transpose=True)
+    assert torch.equal(z.C, coords)
+    vol = torch.zeros(1, Cmid, D // 2, D // 2, D // 2)
+    vol[0][:, c[:, 0], c[:, 1], c[:, 2]] = y.F.t()
+    reft = F.conv_transpose3d(vol, wt.view(2, 2, 2, Cmid, 3).permute(3, 4, 0, 1, 2).contiguous(), stride=2)
+    cf = coords.long()
+    assert torch.allclose(z.F, reft[0][:, cf[:, 0], cf[:, 1], cf[:, 2]].t(), atol=1e-4, rtol=1e-4)
+
+
+def test_sparse_quantize_properties_hypothesis():
+    """A.1 invariants on arbitrary integer clouds: inds = first occurrence of each distinct voxel, keys ascending,
+    inverse reconstructs every row, counts>1 voxels get ignore_label."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 6), st.integers(0, 6), st.integers(0, 6)), min_size=1, max_size=200))
+    def check(rows):
+        c = np.asarray(rows, dtype=np.int64)
+        lab = np.arange(len(c)) % 20
+        inds, labels, inv = ts.sparse_quantize(c, np.zeros((len(c), 1), np.float32), lab, return_index=True,
+                                               return_invs=True)
+        uniq = c[inds]
+        assert len({tuple(r) for r in uniq}) == len(uniq) == len({tuple(r) for r in c})
+        assert np.array_equal(uniq[inv], c)
+        keys = ts.fnv_hash_vec(uniq)
+        assert np.all(keys[1:] > keys[:-1])
+        for j, i in enumerate(inds):                                   # first occurrence
+            assert i == min(k for k in range(len(c)) if tuple(c[k]) == tuple(uniq[j]))
+        cnt = np.bincount(inv, minlength=len(inds))
+        assert np.array_equal(labels[cnt > 1], np.full((cnt > 1).sum(), -100))
+        assert np.array_equal(labels[cnt == 1], lab[inds][cnt == 1])
+    check()
