@@ -56,3 +56,33 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_error_convention_of_the_hot_path_entry_points():
+    """0 = ok, non-zero + thread-local message otherwise; every check runs before the first CUDA call, so unsupported
+    shapes are rejected (never routed to another implementation) even on a box without a GPU."""
+    L = _lib.lib()
+    p = 256          # any non-null 16-byte aligned "pointer": validation does not dereference
+    with pytest.raises(_lib.Ft3dError, match="unsupported shape"):
+        L.conv_pairs_tc(p, p, p, 27, 0, 1000, 20, 64, p, p, None)                 # red not a multiple of 16
+    with pytest.raises(_lib.Ft3dError, match="unsupported shape"):
+        L.conv_pairs_tc(p, p, p, 27, 0, 1000, 64, 320, p, p, None)                # ncols: <= 256 or 384 only
+    with pytest.raises(_lib.Ft3dError, match="identity gather needs K == 1"):
+        L.conv_pairs_tc(p, None, None, 27, 0, 1000, 64, 64, p, p, None)
+    with pytest.raises(_lib.Ft3dError, match="16-byte aligned"):
+        L.conv_pairs_tc(p + 4, p, p, 27, 0, 1000, 64, 64, p, p, None)
+    with pytest.raises(_lib.Ft3dError, match="unsupported shape"):
+        L.conv_wgrad_pairs_tc(p, p, p, p, 27, 0, 64, 512, 1000, p, None)          # cout <= 256
+    with pytest.raises(_lib.Ft3dError, match="at least one row"):
+        L.bn_stats(p, 0, 64, 1e-5, 0.1, p, None, None, None, p, 1 << 20, None)
+    with pytest.raises(_lib.Ft3dError, match="workspace too small"):
+        L.bn_stats(p, 10, 64, 1e-5, 0.1, p, None, None, None, p, 16, None)
+    with pytest.raises(_lib.Ft3dError, match="bad arguments"):
+        L.seg_loss(p, p, 100, 100, -100, None, None, 0.0, None, p, p, p, 1 << 20, None)   # > 64 classes
+    with pytest.raises(_lib.Ft3dError, match="needs teacher logits"):
+        L.seg_loss(p, p, 100, 20, -100, None, None, 0.5, None, p, p, p, 1 << 20, None)
+    # zero-size work is a no-op that succeeds without touching the device
+    L.conv_pairs_tc(p, p, p, 27, 0, 0, 64, 64, p, p, None)
+    L.bn_apply(p, 0, 64, p, p, p, None, 1, p, None, None, None)
+    L.confusion_update(p, p, 0, 20, -100, None, p, None)
+    assert int(L.seg_loss_workspace()) >= 3 * 1024 * 8 and int(L.bn_workspace(256)) > 0
