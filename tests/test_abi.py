@@ -86,3 +86,20 @@ def test_error_convention_of_the_hot_path_entry_points():
     L.bn_apply(p, 0, 64, p, p, p, None, 1, p, None, None, None)
     L.confusion_update(p, p, 0, 20, -100, None, p, None)
     assert int(L.seg_loss_workspace()) >= 3 * 1024 * 8 and int(L.bn_workspace(256)) > 0
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/ft3d.h compiles as C99 and a C program links against libft3d.so (examples/abi_probe.c)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_probe")
+    libdir = os.path.dirname(str(_lib.LIB_PATH))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "abi_probe.c"), "-L", libdir, "-lft3d", "-Wl,-rpath," + libdir,
+                    "-o", exe], check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "ft3d version 100" in out and "table_capacity(1000) = 2048" in out
+    assert "bad shape -> rc 1" in out and "unsupported shape" in out
