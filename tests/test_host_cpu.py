@@ -83,3 +83,24 @@ def test_graph_capacities_only_grow_and_stay_distinct():
             caps = (capacity(a, 1.10, 128, caps[0]), capacity(b, 1.10, 128, caps[1]))
             grows += 1
     assert grows <= 2
+
+
+def test_synthetic_scans_follow_the_survey_shapes_and_are_deterministic():
+    """SURVEY 8(d) generator: KITTI-shaped ~18-22k front-camera points in a 1226x370 image, nuScenes-shaped ~6-9k in
+    1600x900, stress 120k +-2 %; pixel indices strictly inside the image; same seed -> same scan."""
+    import numpy as np
+    from fusiontransformer_b200.synthetic import make_scan
+    want = {"kitti": (18000, 22000, (370, 1226)), "nuscenes": (6000, 9000, (900, 1600)),
+            "stress": (117600, 122400, (370, 1226))}
+    for shape, (lo, hi, hw) in want.items():
+        a, b, c = make_scan(shape, 7), make_scan(shape, 7), make_scan(shape, 8)
+        n = len(a["points"])
+        assert lo <= n <= hi and tuple(a["image_size"]) == hw
+        assert a["points"].dtype == np.float32 and a["feats"].shape == (n, 4) and a["points_img"].shape == (n, 2)
+        assert a["points_img"].min() >= 0 and a["points_img"][:, 0].max() < hw[0] and a["points_img"][:, 1].max() < hw[1]
+        assert np.array_equal(a["feats"][:, :3], a["points"])              # feats = (x, y, z, intensity)
+        assert 0 <= a["seg_labels"].min() and a["seg_labels"].max() < 20
+        assert all(np.array_equal(a[k], b[k]) for k in ("points", "feats", "points_img", "seg_labels"))
+        assert not np.array_equal(a["points"], c["points"])
+        if shape == "kitti":
+            assert a["points"][:, 0].min() > 0                             # front camera: x > 0
