@@ -1032,7 +1032,9 @@ static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_ro
                          float* out, bool stats, float eps, float momentum, float* stat, float* running_mean,
                          float* running_var, const int32_t* valid_rows, void* workspace, size_t workspace_bytes,
                          cudaStream_t s, const char* what) {
-  FT3D_REQUIRE(ppos && out && (kpad == 8 || kpad == 16 || kpad == 32) && ncols >= 4 && ncols % 4 == 0 && ncols <= 1024,
+  // `partial` must hold at least one row even when the map has no pair: absent slots re-read row 0 and discard it
+  FT3D_REQUIRE(partial && ppos && out && (kpad == 8 || kpad == 16 || kpad == 32) && ncols >= 4 && ncols % 4 == 0 &&
+                   ncols <= 1024,
                "%s: bad arguments", what);
   FT3D_REQUIRE(((uintptr_t)partial & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)ppos & 15) == 0,
                "%s: pointers must be 16-byte aligned", what);

@@ -186,6 +186,8 @@ int ft3d_conv_wgrad_tc(const float* a, const float* b, const int32_t* pairs,
  *                         conv3d kernel_size 1 == F.matmul) whose partial_out IS the result.
  *   ft3d_conv_reduce    : out[row,:] = sum_j partial[ppos[row,j],:] over the row's compacted positions, i.e. in
  *                         ascending offset order (deterministic, no atomics, every output row written once).
+ *                         `partial` must hold at least one row even for a map without pairs (absent slots re-read
+ *                         row 0 and discard it).
  *   ft3d_conv_reduce_bn : the same pass also folds the per-channel sum / sum of squares of the rows it writes and
  *                         leaves this layer's BatchNorm training statistics in stat (see ft3d_bn_stats).
  *   forward: gather_col 0, ppos of ft3d_kmap_pairs;   dgrad / transposed conv: gather_col 1, ppos of
