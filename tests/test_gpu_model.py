@@ -100,17 +100,31 @@ def test_train_step_gradients(monkeypatch, small_batch, fusion, mode, tol):
         assert cos > 0.9 and worst < 1.0, (cos, worst_name, worst)
 
 
-def test_reference_model_files_run_unmodified():
-    """If the reference tree is present (dev container only), its own spvcnn.py / utils.py import against the alias."""
-    ref = "/root/reference/FusionTransformer/models/spvcnn.py"
-    if not os.path.exists(ref):
-        pytest.skip("reference tree not present on this box")
-    import sys
+@pytest.mark.parametrize("fusion", ["middle", "early"])
+@pytest.mark.parametrize("mode,tol", [("f32", 2e-4), ("tc", 1e-2)])
+def test_logits_match_reference_run_fixture(monkeypatch, fusion, mode, tol):
+    """tests/golden/ref_model_small.npz holds the outputs of the REFERENCE'S OWN spvcnn.py / utils.py /
+    middle_fusion.py / early_fusion.py executed on the CPU (make_reference_model_golden.py); the CUDA path must
+    reproduce its eval-mode and train-mode logits and loss within the north-star tolerance."""
     import fusiontransformer_b200 as ft
-    ft.install_as_torchsparse()
-    sys.path.insert(0, "/root/reference")
-    try:
-        from FusionTransformer.models.spvcnn import SPVCNN as RefSPVCNN
-    finally:
-        sys.path.pop(0)
-    assert RefSPVCNN is not None
+    from tests.golden.make_golden import model_small_img_feats
+    monkeypatch.setenv("FT3D_CONV", mode)
+    gold = np.load(os.path.join(GOLD, "ref_model_small.npz"))
+    _, m = _models(fusion)
+    coords = torch.from_numpy(gold["coords"]).cuda()
+    feats = torch.from_numpy(gold["feats"]).cuda()
+    img = model_small_img_feats(coords.shape[0]).cuda()
+    m.eval()
+    with torch.no_grad():
+        out = m(ft.SparseTensor(feats, coords), img)
+    assert rel_l2(out["lidar_seg_logit"], torch.from_numpy(gold[fusion + "_eval_logits"])) < tol
+    m.train()
+    m.dropout.p = 0.0
+    out = m(ft.SparseTensor(feats, coords), img)
+    loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], torch.from_numpy(gold["labels"]).cuda())
+    loss.backward()
+    assert rel_l2(out["lidar_seg_logit"], torch.from_numpy(gold[fusion + "_train_logits"])) < tol
+    assert abs(loss.item() - float(gold[fusion + "_train_loss"])) < tol * max(1.0, float(gold[fusion + "_train_loss"]))
+    if mode == "f32":
+        assert rel_l2(m.linear.weight.grad, torch.from_numpy(gold[fusion + "_grad_linear_weight"])) < 2e-3
+        assert rel_l2(m.up4[1][1].net[3].kernel.grad, torch.from_numpy(gold[fusion + "_grad_up4_last_kernel"])) < 2e-3
