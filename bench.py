@@ -158,7 +158,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="nuscenes", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: BASELINE.json configs[1] (nuscenes) at --gpus 1, configs[2] (kitti, the data-parallel "
+                         "config) at --gpus > 1; 'stress' = configs[4]")
     ap.add_argument("--batch", type=int, default=0, help="scans per GPU per step (default: the workload's)")
     ap.add_argument("--fusion", default="middle", choices=["none", "middle", "early"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -177,6 +179,8 @@ def main():
                     help="build each batch's geometry inside its own step (host reads stall the launch queue)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload is None:
+        args.workload = "nuscenes" if args.gpus <= 1 else "kitti"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -378,7 +382,9 @@ def main():
     if not args.no_roofline:             # every rank runs the pass (the steps contain collectives); rank 0 reports
         pk = peaks()
         L.profile, conv_engine.WORK_LOG = [], []
-        L.profile_repeat = {"conv_pairs_tc": 4}      # idempotent: P is rewritten with the same values
+        # idempotent launches (outputs rewritten with the same values; conv_os's repeats also re-apply the BatchNorm
+        # running-statistics momentum update, which training-mode steps never read)
+        L.profile_repeat = {"conv_pairs_tc": 4, "conv_os": 4}
         nprof = min(args.steps, 5)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -402,7 +408,7 @@ def main():
         # convolutions all run through it.  Algorithmic work of one launch (DESIGN.md "Roofline accounting"):
         #   flops = 2 L red ncols ;  bytes = 2 (rows_in red + K red ncols) + 4 rows_out ncols + 8 L   (SURVEY 8(d), bf16
         #   operands, fp32 result).  Both bounds are evaluated per launch; the binding one is reported.
-        dom = "conv_pairs_tc"
+        dom = "conv_os" if "conv_os" in tot else "conv_pairs_tc"
         convs = [w for w in work if w["kind"] == dom]
         if dom in tot and convs:
             t_s = tot[dom][0] * 1e-3
@@ -414,7 +420,7 @@ def main():
             ach, peak, unit = (fl / t_s / 1e12, pk["tf_sus"], "TFLOP/s") if bound == "tensor" else \
                               (by / t_s / 1e9, pk["hbm"], "GB/s")
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "traffic_conv_pairs_tc.json")
+            tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % dom)
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
@@ -427,7 +433,7 @@ def main():
                         "tflops": fl / t_s / 1e12, "gbs": by / t_s / 1e9,
                         "share_of_step": tot[dom][0] / nprof / (ms / args.steps),
                         "share_of_kernel_time": tot[dom][0] / max(sum(v[0] for v in tot.values()), 1e-9),
-                        "note": "time = CUDA events on the launching stream around every conv_pairs_tc call (4 back-to-back "
+                        "note": "time = CUDA events on the launching stream around every " + dom + " call (4 back-to-back "
                                 "launches of it between the two events, / 4: a single ~20 us launch would carry ~8 us "
                                 "of event overhead), summed over %d separately profiled steps launched kernel by kernel; share_of_step = that time per "
                                 "step / the graph-replayed ms_per_step (kernels of other streams overlap it); "

@@ -15,15 +15,13 @@ import torch
 from . import ops
 
 
-_environ = os.environ          # os.environ.get() encodes/decodes on every call; the raw mapping lookup is 10x cheaper
-_KEY_CONV, _KEY_ALGO = os.environ.encodekey("FT3D_CONV"), os.environ.encodekey("FT3D_CONV_ALGO")
+_environ = os.environ
 
 
 def mode() -> str:
-    m = _environ._data.get(_KEY_CONV)
+    m = _environ.get("FT3D_CONV")
     if m is None:
         return "tc"
-    m = os.environ.decodevalue(m)
     if m not in ("tc", "f32"):
         raise ValueError("FT3D_CONV must be 'tc' or 'f32'")
     return m
@@ -71,9 +69,9 @@ def pairs_ok(cin: int, cout: int) -> bool:
     """Both the forward (red=cin, ncols=cout), the dgrad (red=cout, ncols=cin) and the wgrad shape must be covered."""
     def gemm_ok(red, ncols):
         return red % 16 == 0 and 16 <= red <= 512 and ncols % 32 == 0 and (32 <= ncols <= 256 or ncols == 384)
-    algo = _environ._data.get(_KEY_ALGO)
-    return (mode() == "tc" and (algo is None or os.environ.decodevalue(algo) == "pairs") and gemm_ok(cin, cout)
-            and gemm_ok(cout, cin) and cout <= 256)
+    algo = _environ.get("FT3D_CONV_ALGO")
+    return (mode() == "tc" and algo in (None, "os", "pairs") and gemm_ok(cin, cout) and gemm_ok(cout, cin)
+            and cout <= 256)
 
 
 def pairs_partial(x16, kmap, kernel, role: str):
@@ -98,6 +96,26 @@ def pairs_partial(x16, kmap, kernel, role: str):
         WORK_LOG.append(dict(kind="conv_pairs_tc", pairs=L, red=red, ncols=ncols, rows=ppos.shape[0], K=K,
                              rows_in=x16.shape[0]))
     return ops.conv_pairs_tc(x16, pairs, offsets, K, gcol, L, w, wt, owner=kernel), ppos, ncols
+
+
+def os_enabled() -> bool:
+    """FT3D_CONV_ALGO: unset / "os" = output-stationary conv_os for forward, dgrad and transposed convolutions;
+    "pairs" = the pair-major GEMM + sorted scatter of csrc/conv_pairs_tc.cu."""
+    algo = _environ.get("FT3D_CONV_ALGO")
+    return algo is None or algo == "os"
+
+
+def os_conv(x16, kmap, kernel, role: str, bn=None):
+    """Output-stationary tcgen05 convolution of one layer (csrc/conv_os.cu): -> (y f32 [rows, ncols], stat or None).
+    ``bn`` = (eps, momentum, running_mean, running_var): BatchNorm training statistics from the epilogue."""
+    plan, wt, kflip, n_rows = kmap.os_args(role)
+    w = kernel.detach()
+    cin, cout = w.shape[-2], w.shape[-1]
+    red, ncols = (cout, cin) if wt else (cin, cout)
+    if WORK_LOG is not None:
+        WORK_LOG.append(dict(kind="conv_os", pairs=kmap.num_pairs(), red=red, ncols=ncols, rows=n_rows, K=kmap.K,
+                             rows_in=x16.shape[0], passes=plan.passes()))
+    return ops.conv_os(x16, plan, w, wt, kflip, n_rows, owner=kernel, bn=bn)
 
 
 def pairs_conv(x16, kmap, kernel, role: str):

@@ -1,0 +1,600 @@
+// Output-stationary sparse convolution on tcgen05 tensor cores, with the BatchNorm statistics in the epilogue.
+//
+//     out[j,:] = sum_k  in[ nbr_k(j), : ] @ B_k          bf16 operands, fp32 accumulation in TMEM
+//
+// A CTA owns tiles of 128 output rows taken from the mask-sorted schedule of os_plan.cu: for every offset k that at
+// least one row of the tile uses (a "pass") it gathers the 128 neighbour rows (absent neighbours are zero rows),
+// multiplies them with B_k and ACCUMULATES IN TMEM across passes in ascending k -- the reference's own summation
+// order.  A finished tile is read from TMEM once and every output row is written exactly once, complete: there is no
+// partial-row buffer, no second reduction pass, no atomics, and the result does not depend on scheduling.
+// While the rows pass through the epilogue their per-channel sum and sum of squares are folded per CTA, and the last
+// CTA to finish turns the partials into this layer's BatchNorm training statistics (mean, rstd, running stats): the
+// activation is never re-read for its statistics and no finalize kernel is launched.
+//
+// Warp roles (320 threads, one persistent CTA per SM, tiles t = blockIdx.x, += gridDim.x):
+//   0      producer, TMA mode (default): the 32 lanes issue 32 x cp.async.bulk.tensor.2d ... tile::gather4 (4 rows x
+//          128 B each, hardware 128B swizzle, out-of-range row index -1 => zero fill) = one 128 x 64 A block, and lane 0
+//          adds the cp.async.bulk of the matching B block onto the same mbarrier (complete_tx bytes);
+//   0-3,4  producers, LDGSTS mode (FT3D_OS_GATHER=ldgsts): 16-byte cp.async row pieces + bulk B, as conv_pairs_tc.cu;
+//   5      MMA issuer: tcgen05.mma 128 x ncols x 16 into accumulator buffer (tile & 1); tcgen05.commit frees ring
+//          slots and hands the accumulator to the epilogue;
+//   6-9    epilogue: tcgen05.ld -> per-warp staging transpose -> 128-byte row segments to out[row] + statistics.
+// The A/B ring runs across pass and tile boundaries; two TMEM accumulators (ncols <= 256) let the gathers and MMAs
+// of tile t+1 run under the epilogue of tile t.
+#include <cuda.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "bn_common.cuh"
+
+namespace ft3d {
+using namespace tc;
+
+constexpr int kOsThreads = 320;
+constexpr int kOsMaxSlots = 10;
+constexpr int kOsStageFloats = 32 * 36;        // one epilogue warp: 32 rows x (32 + 4 pad) floats
+constexpr int kOsProducers = 128;              // warps 0-3
+
+struct OsHeader {
+  uint64_t full[kOsMaxSlots];
+  uint64_t empty[kOsMaxSlots];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  int32_t idx[2][kTileRows];                   // LDGSTS mode: gather indices of the pass being issued
+};
+
+struct OsArgs {
+  const __nv_bfloat16* in;
+  const int4* units;          // [U][2] int4 = {first pass, passes, tile, chunks, chunk, scratch base, -, -}
+  const int32_t* num;         // {P, U, S, cap}
+  const int32_t* out_row;
+  const int32_t* pass_k;
+  const int32_t* pass_idx;
+  const uint8_t* wpacked;
+  float* out;
+  float* partials;            // statistics: [gridDim.x][2][ncols]; nullptr = no statistics
+  float* scratch;             // [S][128][ncols] partial tiles of split tiles (folded by conv_os_fold_kernel)
+  const int32_t* valid_rows;
+  unsigned long long* trace;  // nullable: per CTA 8 x u64 (globaltimer stamps and counts), tools/conv_os_probe.py
+  int64_t n_out;
+  int unit_cap, K, kflip, red, ncols, nslots, tcols, nbuf;
+};
+
+__device__ __forceinline__ void os_cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void os_cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void os_named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned long long os_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// TMA gather4: rows {r0..r3} x 64 bf16 starting at column `col` of the 2-D tensor -> 4 consecutive 128-byte rows of
+// a 128B-swizzled block at dst (negative / out-of-range rows are filled with zeros; the transaction always counts
+// 512 bytes on the mbarrier).
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap* tmap, int col, int r0, int r1, int r2,
+                                            int r3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst_smem),
+      "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// walks the passes of this CTA's work units u = first, first + step, ... (units without passes are skipped); the
+// record of the following unit is requested one unit ahead so that crossing a unit boundary costs no L2 round trip
+struct OsPassIter {
+  const int4* units;
+  int U, u, step, begin, n, q, nb, nn;
+  __device__ __forceinline__ void fetch_next() {
+    nb = nn = 0;
+    if (u + step < U) {
+      const int4 un = __ldg(units + 2 * (int64_t)(u + step));
+      nb = un.x; nn = un.y;
+    }
+  }
+  __device__ __forceinline__ void init(const int4* units_, int U_, int first, int step_) {
+    units = units_; U = U_; u = first; step = step_; begin = n = q = nb = nn = 0;
+    if (u < U) {
+      const int4 un = __ldg(units + 2 * (int64_t)u);
+      begin = un.x; n = un.y;
+      fetch_next();
+      while (u < U && n == 0) advance();
+    }
+  }
+  __device__ __forceinline__ void advance() {
+    u += step; begin = nb; n = nn; q = 0;
+    if (u < U) fetch_next();
+  }
+  __device__ __forceinline__ bool valid() const { return u < U; }
+  __device__ __forceinline__ int pass() const { return begin + q; }
+  __device__ __forceinline__ void next() {
+    if (++q >= n) {
+      advance();
+      while (u < U && n == 0) advance();
+    }
+  }
+};
+
+template <bool TMA>
+__global__ void __launch_bounds__(kOsThreads)
+conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int red = a.red, ncols = a.ncols, nslots = a.nslots;
+  const int nkb = (red + 63) / 64;
+  const int b_bytes = ncols * kBlockRowBytes;
+  const int stage_bytes = kBlockBytes + b_bytes;
+  float* staging = reinterpret_cast<float*>(smem + (size_t)nslots * stage_bytes);
+  float* sstat = staging + 4 * kOsStageFloats;                                   // [4 warps][2][ncols]
+  OsHeader* hdr = reinterpret_cast<OsHeader*>(sstat + 4 * 2 * ncols);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int step = (int)gridDim.x, first = (int)blockIdx.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < nslots; ++s) {
+      mbar_init(&hdr->full[s], TMA ? 1 : kOsProducers + 1);
+      mbar_init(&hdr->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&hdr->acc_full[b], 1);
+      mbar_init(&hdr->acc_empty[b], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)(a.nbuf * a.tcols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_enter();      // launch, barrier and TMEM set-up ran under the predecessor's tail; every global read is below
+  const uint32_t tmem_base = hdr->tmem_base;
+  int U = __ldg(a.num + 1);
+  if (U > a.unit_cap) U = a.unit_cap;
+  unsigned long long* tr = a.trace != nullptr ? a.trace + (size_t)blockIdx.x * 8 : nullptr;
+  if (tr != nullptr && tid == 0) tr[0] = os_now();
+
+  if (TMA && warp < 4) {
+    // ------------------------------------------------------------------ producers: TMA gather4 (A) + bulk copy (B)
+    // A 128 x 64 block is 32 gather4 loads; a warp issues them lane by lane (the operands of a TMA instruction are
+    // warp-uniform), so the four producer warps each take a quarter of the block: lanes 0-7 of warp w load rows
+    // w*32 + 4*lane .. +3.  Warp 0 also arms the stage's mbarrier with the byte count and adds the B block.
+    OsPassIter it;
+    it.init(a.units, U, first, step);
+    int k_n = 0;
+    int4 r_n = make_int4(-1, -1, -1, -1);
+    const int sub = lane & 7;
+    if (it.valid()) {
+      k_n = __ldg(a.pass_k + it.pass());
+      r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * kTileRows) + warp * 8 + sub);
+    }
+    uint32_t cnt = 0, npass = 0;
+    while (it.valid()) {
+      const int k = a.kflip ? a.K - 1 - k_n : k_n;
+      const int4 r4 = r_n;
+      it.next();
+      ++npass;
+      if (it.valid()) {                                    // next pass's indices travel under this pass's issue
+        k_n = __ldg(a.pass_k + it.pass());
+        r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * kTileRows) + warp * 8 + sub);
+      }
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        const int slot = (int)(cnt % (uint32_t)nslots);
+        const uint32_t use = cnt / (uint32_t)nslots;
+        if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
+        uint8_t* st = smem + (size_t)slot * stage_bytes;
+        if (warp == 0 && lane == 0) {
+          mbar_arrive_expect_tx(&hdr->full[slot], (uint32_t)(kBlockBytes + b_bytes));
+          bulk_g2s(st + kBlockBytes, a.wpacked + ((size_t)k * nkb + kb) * b_bytes, (uint32_t)b_bytes, &hdr->full[slot]);
+        }
+        if (lane < 8)
+          tma_gather4(smem_u32(st) + (uint32_t)(warp * 8 + lane) * 512u, &tmap, kb * 64, r4.x, r4.y, r4.z, r4.w,
+                      &hdr->full[slot]);
+      }
+    }
+    if (tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = npass;
+  } else if (!TMA && warp < 4) {
+    // ------------------------------------------------------------------ producers: 16-byte cp.async row pieces
+    OsPassIter it;
+    it.init(a.units, U, first, step);
+    uint32_t cnt = 0, np = 0;
+    int g_n = it.valid() ? __ldg(a.pass_idx + (int64_t)it.pass() * kTileRows + tid) : -1;
+    while (it.valid()) {
+      const int ib = (int)(np & 1);
+      hdr->idx[ib][tid] = g_n;
+      it.next();
+      ++np;
+      if (it.valid()) g_n = __ldg(a.pass_idx + (int64_t)it.pass() * kTileRows + tid);
+      os_named_bar_sync(1, kOsProducers);
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        const int slot = (int)(cnt % (uint32_t)nslots);
+        const uint32_t use = cnt / (uint32_t)nslots;
+        if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
+        const uint32_t base = smem_u32(smem + (size_t)slot * stage_bytes);
+        const int width = red - kb * 64 < 64 ? red - kb * 64 : 64;
+        const int nchunk = width >> 3;
+        for (int q = tid; q < kTileRows * 8; q += kOsProducers) {
+          const int r = q >> 3, c = q & 7;
+          const int g = hdr->idx[ib][r];
+          const bool live = g >= 0 && c < nchunk;
+          const __nv_bfloat16* p = a.in + (live ? (int64_t)g * red + kb * 64 + c * 8 : 0);
+          os_cp_async_16(base + r * kBlockRowBytes + ((c ^ (r & 7)) << 4), p, live ? 16u : 0u);
+        }
+        os_cp_async_arrive_noinc(&hdr->full[slot]);
+      }
+    }
+    if (tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = np;
+  } else if (!TMA && warp == 4) {
+    // ------------------------------------------------------------------ weight loader (LDGSTS mode)
+    if (lane == 0) {
+      OsPassIter it;
+      it.init(a.units, U, first, step);
+      uint32_t cnt = 0;
+      for (; it.valid(); it.next()) {
+        int k = __ldg(a.pass_k + it.pass());
+        if (a.kflip) k = a.K - 1 - k;
+        for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+          const int slot = (int)(cnt % (uint32_t)nslots);
+          const uint32_t use = cnt / (uint32_t)nslots;
+          if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
+          mbar_arrive_expect_tx(&hdr->full[slot], (uint32_t)b_bytes);
+          bulk_g2s(smem + (size_t)slot * stage_bytes + kBlockBytes, a.wpacked + ((size_t)k * nkb + kb) * b_bytes,
+                   (uint32_t)b_bytes, &hdr->full[slot]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const int nsplit = ncols > 256 ? 2 : 1;
+      const int ncw = ncols / nsplit;
+      const uint32_t idesc = umma_idesc_bf16(128, ncw, 0, 0);
+      uint32_t cnt = 0, use_acc = 0;
+      int np_n = first < U ? __ldg(a.units + 2 * (int64_t)first).y : 0;
+      for (int u = first; u < U; u += step) {
+        const int np = np_n;
+        if (u + step < U) np_n = __ldg(a.units + 2 * (int64_t)(u + step)).y;
+        if (np == 0) continue;
+        const int buf = (int)(use_acc % (uint32_t)a.nbuf);
+        const uint32_t ub = use_acc / (uint32_t)a.nbuf;
+        if (ub > 0) mbar_wait(&hdr->acc_empty[buf], (ub & 1) ^ 1);     // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * a.tcols);
+        for (int q = 0; q < np; ++q) {
+          for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+            const int slot = (int)(cnt % (uint32_t)nslots);
+            const uint32_t use = cnt / (uint32_t)nslots;
+            mbar_wait(&hdr->full[slot], use & 1);
+            if (!TMA) fence_proxy_async_smem();            // cp.async (generic proxy) data -> tensor-core reads
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)slot * stage_bytes);
+            const uint32_t b_addr = a_addr + kBlockBytes;
+            const int ksteps = (red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4;
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t da = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+              for (int c = 0; c < nsplit; ++c)
+                umma_bf16(tmem_d + (uint32_t)(c * ncw), da,
+                          smem_desc_sw128(b_addr + c * ncw * kBlockRowBytes + kk * 32, 16, 1024), idesc,
+                          (q | kb | kk) != 0);
+            }
+            umma_commit(&hdr->empty[slot]);
+          }
+        }
+        umma_commit(&hdr->acc_full[buf]);
+        ++use_acc;
+      }
+      if (tr != nullptr) tr[2] = os_now();
+    }
+  } else if (warp >= 6) {
+    // ------------------------------------------------------------------ epilogue (TMEM quadrant = warp % 4)
+    const int q = warp & 3, te = tid - 6 * 32;
+    float* st = staging + (size_t)(warp - 6) * kOsStageFloats;
+    float* ws1 = sstat + (size_t)(warp - 6) * 2 * ncols;
+    float* ws2 = ws1 + ncols;
+    const bool stats = a.partials != nullptr;
+    if (stats)
+      for (int c = lane; c < 2 * ncols; c += 32) ws1[c] = 0.f;
+    // rows beyond the real row count of a capacity-padded output stay exactly zero (graph.py)
+    if (a.valid_rows != nullptr) {
+      const int64_t v = (int64_t)__ldg(a.valid_rows);
+      const int c4 = ncols >> 2;
+      for (int64_t row = v + first; row < a.n_out; row += step)
+        for (int c = te; c < c4; c += 128)
+          *reinterpret_cast<float4*>(a.out + row * ncols + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    uint32_t use_acc = 0, nunits = 0, nsplit_units = 0;
+    int4 u0_n = make_int4(0, 0, 0, 1), u1_n = make_int4(0, 0, 0, 0);
+    if (first < U) u0_n = __ldg(a.units + 2 * (int64_t)first), u1_n = __ldg(a.units + 2 * (int64_t)first + 1);
+    for (int u = first; u < U; u += step, ++nunits) {
+      const int4 u0 = u0_n, u1 = u1_n;                     // {first pass, passes, tile, chunks}, {chunk, scratch base}
+      if (u + step < U) u0_n = __ldg(a.units + 2 * (int64_t)(u + step)), u1_n = __ldg(a.units + 2 * (int64_t)(u + step) + 1);
+      const int tile = u0.z, chunks = u0.w;
+      const int my_row = __ldg(a.out_row + (int64_t)tile * kTileRows + q * 32 + lane);
+      if (u0.y == 0) {                                     // rows without any neighbour: the result is zero
+        if (my_row >= 0)
+          for (int c = 0; c < ncols; c += 4)
+            *reinterpret_cast<float4*>(a.out + (int64_t)my_row * ncols + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      const int buf = (int)(use_acc % (uint32_t)a.nbuf);
+      mbar_wait(&hdr->acc_full[buf], (use_acc / (uint32_t)a.nbuf) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * a.tcols) + ((uint32_t)(q * 32) << 16);
+      // split tile: this unit's partial rows go to its scratch slot, [slot][tile row][ncols]
+      float* part = chunks > 1 ? a.scratch + ((size_t)(u1.y + u1.x) * kTileRows + q * 32) * ncols : nullptr;
+      nsplit_units += chunks > 1 ? 1u : 0u;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(st + lane * 36 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        __syncwarp();
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {                   // a warp store = 4 rows x 128 contiguous bytes
+          const int r = i8 * 4 + (lane >> 3);
+          const int row = __shfl_sync(0xffffffffu, my_row, r);
+          const float4 val = *reinterpret_cast<const float4*>(st + r * 36 + (lane & 7) * 4);
+          if (part != nullptr) {
+            *reinterpret_cast<float4*>(part + (size_t)r * ncols + c0 + (lane & 7) * 4) = val;
+          } else if (row >= 0) {
+            *reinterpret_cast<float4*>(a.out + (int64_t)row * ncols + c0 + (lane & 7) * 4) = val;
+            s1.x += val.x; s1.y += val.y; s1.z += val.z; s1.w += val.w;
+            s2.x = fmaf(val.x, val.x, s2.x); s2.y = fmaf(val.y, val.y, s2.y);
+            s2.z = fmaf(val.z, val.z, s2.z); s2.w = fmaf(val.w, val.w, s2.w);
+          }
+        }
+        if (stats && part == nullptr) {                    // fold the 4 row groups (lane >> 3), lanes 0-7 keep the sums
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+          }
+          if (lane < 8) {
+            float4* p1 = reinterpret_cast<float4*>(ws1 + c0 + lane * 4);
+            float4* p2 = reinterpret_cast<float4*>(ws2 + c0 + lane * 4);
+            float4 x1 = *p1, x2 = *p2;
+            x1.x += s1.x; x1.y += s1.y; x1.z += s1.z; x1.w += s1.w;
+            x2.x += s2.x; x2.y += s2.y; x2.z += s2.z; x2.w += s2.w;
+            *p1 = x1; *p2 = x2;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(&hdr->acc_empty[buf]);
+      ++use_acc;
+    }
+    if (tr != nullptr && te == 0) tr[3] = os_now(), tr[6] = nunits | ((unsigned long long)nsplit_units << 32);
+    if (stats) {
+      // CTA partial row = sum of the four warps in fixed order; col_finalize_kernel (bn_common.cuh, its own tiny
+      // launch: channels/4 CTAs read the <= 148 partial rows in ONE L2 round trip) folds them in double.  A "last CTA
+      // folds everything" tail was measured at 7.5 us per layer: 37 dependent L2 round trips on one SM.
+      os_named_bar_sync(2, 128);
+      float* prow = a.partials + (size_t)blockIdx.x * 2 * ncols;
+      for (int c = te; c < 2 * ncols; c += 128)
+        prow[c] = (sstat[c] + sstat[2 * ncols + c]) + (sstat[4 * ncols + c] + sstat[6 * ncols + c]);
+    }
+    if (tr != nullptr && te == 0) tr[4] = os_now();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)(a.nbuf * a.tcols));
+}
+
+// Fold of the split tiles: out[row] = sum of the tile's unit partials IN UNIT ORDER (ascending offsets), one CTA per
+// split tile.  All loads of a thread are independent (rows x units), so the kernel is one or two L2 round trips long;
+// it touches only the 8-15 % of the rows that live in heavy tiles.  With STATS each CTA adds its partial statistics row
+// behind conv_os's (CTAs without a tile publish zeros, so the finalize reads a fixed number of rows).
+template <bool STATS>
+__global__ void __launch_bounds__(kColThreads)
+conv_os_fold_kernel(const int4* __restrict__ split_tiles, const int32_t* __restrict__ num,
+                    const int32_t* __restrict__ out_row, const float* __restrict__ scratch, int ncols,
+                    float* __restrict__ out, float* __restrict__ partials) {
+  pdl_enter();
+  __shared__ float4 s_stage[STATS ? kColStageFloat4 : 1];
+  __shared__ int s_rows[kTileRows];
+  const int ns = __ldg(num + 4);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if ((int)blockIdx.x < ns) {
+    const int4 sp = __ldg(split_tiles + blockIdx.x);       // {tile, units, first scratch slot, -}
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int r = tid; r < kTileRows; r += blockDim.x * blockDim.y) s_rows[r] = __ldg(out_row + (int64_t)sp.x * kTileRows + r);
+    __syncthreads();
+    const int ch = threadIdx.x * 4;
+    const float* p0 = scratch + (size_t)sp.z * kTileRows * ncols + ch;
+    const size_t cstride = (size_t)kTileRows * ncols;
+    constexpr int RB = 4;
+    for (int r0 = threadIdx.y; r0 < kTileRows; r0 += RB * blockDim.y) {
+      float4 x[RB][4];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int r = r0 + i * blockDim.y;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          x[i][c] = (r < kTileRows && c < sp.y) ? __ldg(reinterpret_cast<const float4*>(p0 + c * cstride + (size_t)r * ncols))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int r = r0 + i * blockDim.y;
+        if (r >= kTileRows) break;
+        const int row = s_rows[r];
+        if (row < 0) continue;
+        float4 acc = x[i][0];
+#pragma unroll
+        for (int c = 1; c < 4; ++c)
+          if (c < sp.y) add4(acc, x[i][c]);
+        *reinterpret_cast<float4*>(out + (int64_t)row * ncols + ch) = acc;
+        if (STATS) {
+          add4(s1, acc);
+          fma4(s2, acc, acc);
+        }
+      }
+    }
+  }
+  if (STATS) col_publish(s1, s2, partials, ncols, s_stage);
+}
+
+static int os_tmem_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [n_rows][red], box = 64 columns x 1 row, 128B swizzle: the descriptor of the gather4 loads
+static int make_row_tmap(CUtensorMap* tm, const void* base, int64_t n_rows, int red) {
+  EncodeTiledFn fn = encode_fn();
+  FT3D_REQUIRE(fn != nullptr, "ft3d_conv_os: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)red, (cuuint64_t)(n_rows > 0 ? n_rows : 1)};
+  cuuint64_t strides[1] = {(cuuint64_t)red * 2};
+  cuuint32_t box[2] = {64, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FT3D_REQUIRE(r == CUDA_SUCCESS, "ft3d_conv_os: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return FT3D_OK;
+}
+
+static int os_gather_mode() {      // 1 = TMA gather4 (default), 0 = LDGSTS; read per call (a getenv is ~50 ns)
+  const char* e = getenv("FT3D_OS_GATHER");
+  return (e != nullptr && (e[0] == 'l' || e[0] == 'L')) ? 0 : 1;
+}
+
+constexpr int kOsMaxCtas = kNumSMs;
+
+static int64_t os_fold_ctas(int64_t scratch_slots) { return (scratch_slots + 1) / 2; }     // a split tile has >= 2 units
+static size_t os_partials_bytes(int ncols, int64_t scratch_slots) {
+  return align_up((size_t)(kOsMaxCtas + os_fold_ctas(scratch_slots)) * 2 * (size_t)ncols * sizeof(float), 256);
+}
+
+}  // namespace ft3d
+
+using namespace ft3d;
+
+extern "C" {
+
+size_t ft3d_conv_os_workspace(int32_t ncols, int64_t scratch_slots) {
+  return os_partials_bytes(ncols, scratch_slots) +
+         align_up((size_t)scratch_slots * tc::kTileRows * (size_t)ncols * sizeof(float), 256);
+}
+
+int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const int32_t* split_tiles,
+                 const int32_t* num, const int32_t* out_row, const int32_t* pass_k, const int32_t* pass_idx,
+                 int64_t unit_cap, int64_t tiles, int64_t scratch_slots, int32_t K, int32_t kflip, int32_t red,
+                 int32_t ncols, const void* wpacked, float* out, int64_t n_out, const int32_t* valid_rows, float eps,
+                 float momentum, float* stat, float* running_mean, float* running_var, void* workspace,
+                 size_t workspace_bytes, void* trace, ft3d_stream_t stream) {
+  if (tiles == 0 || n_out == 0) return FT3D_OK;
+  FT3D_REQUIRE(in_bf16 && units && num && out_row && pass_k && pass_idx && wpacked && out && K > 0 && K <= 32 &&
+                   n_in > 0 && unit_cap >= tiles && scratch_slots >= 0 && (scratch_slots == 0 || split_tiles),
+               "ft3d_conv_os: bad arguments");
+  FT3D_REQUIRE(red >= 16 && red % 16 == 0 && red <= 512 && ncols >= 32 && ncols % 32 == 0 &&
+                   (ncols <= 256 || ncols == 384),
+               "ft3d_conv_os: unsupported shape red=%d ncols=%d", red, ncols);
+  FT3D_REQUIRE(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 &&
+                   ((uintptr_t)pass_idx & 15) == 0 && ((uintptr_t)units & 15) == 0 && ((uintptr_t)split_tiles & 15) == 0,
+               "ft3d_conv_os: pointers must be 16-byte aligned");
+  const bool stats = stat != nullptr;
+  FT3D_REQUIRE((!stats && scratch_slots == 0) ||
+                   (workspace && ((uintptr_t)workspace & 255) == 0 &&
+                    workspace_bytes >= ft3d_conv_os_workspace(ncols, scratch_slots)),
+               "ft3d_conv_os: needs a 256-byte aligned workspace of ft3d_conv_os_workspace(ncols, slots) bytes");
+  FT3D_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "ft3d_conv_os: running stats go together");
+  OsArgs a;
+  a.in = (const __nv_bfloat16*)in_bf16;
+  a.units = (const int4*)units;
+  a.num = num;
+  a.out_row = out_row;
+  a.pass_k = pass_k;
+  a.pass_idx = pass_idx;
+  a.wpacked = (const uint8_t*)wpacked;
+  a.out = out;
+  a.partials = stats ? (float*)workspace : nullptr;
+  a.scratch = workspace ? (float*)((char*)workspace + os_partials_bytes(ncols, scratch_slots)) : nullptr;
+  a.valid_rows = valid_rows;
+  a.trace = (unsigned long long*)trace;
+  a.n_out = n_out;
+  a.unit_cap = (int)unit_cap; a.K = K; a.kflip = kflip; a.red = red; a.ncols = ncols;
+  a.tcols = os_tmem_cols(ncols);
+  a.nbuf = 2 * a.tcols <= 512 ? 2 : 1;
+  const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes;
+  const int fixed = 4 * kOsStageFloats * (int)sizeof(float) + 8 * ncols * (int)sizeof(float) + (int)sizeof(OsHeader) + 1024 + 64;
+  int nslots = (227 * 1024 - fixed) / stage_bytes;
+  if (nslots > kOsMaxSlots) nslots = kOsMaxSlots;
+  FT3D_REQUIRE(nslots >= 2, "ft3d_conv_os: red=%d ncols=%d does not fit shared memory", red, ncols);
+  a.nslots = nslots;
+  const int smem_bytes = fixed + nslots * stage_bytes;
+  const unsigned grid = (unsigned)(tiles < kOsMaxCtas ? tiles : kOsMaxCtas);
+  CUtensorMap tm;
+  const bool tma = os_gather_mode() == 1;
+  if (tma) {
+    int rc = make_row_tmap(&tm, in_bf16, n_in, red);
+    if (rc) return rc;
+  } else {
+    memset(&tm, 0, sizeof(tm));
+  }
+  static int configured = 0;
+  if (!configured) {
+    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (tma)
+    launch_pdl(conv_os_kernel<true>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
+  else
+    launch_pdl(conv_os_kernel<false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
+  int nparts = (int)grid;
+  if (scratch_slots > 0) {                       // the schedule has split tiles: fold their unit partials
+    const int fgrid = (int)os_fold_ctas(scratch_slots);
+    const int cv = ncols / 4;
+    int ry = kColThreads / cv;
+    if (ry < 1) ry = 1;
+    if (ry > 32) ry = 32;
+    float* fparts = stats ? a.partials + (size_t)grid * 2 * ncols : nullptr;
+    if (stats)
+      launch_pdl(conv_os_fold_kernel<true>, dim3(fgrid), dim3(cv, ry), 0, s, (const int4*)split_tiles, num, out_row,
+                 (const float*)a.scratch, (int)ncols, out, fparts);
+    else
+      launch_pdl(conv_os_fold_kernel<false>, dim3(fgrid), dim3(cv, ry), 0, s, (const int4*)split_tiles, num, out_row,
+                 (const float*)a.scratch, (int)ncols, out, fparts);
+    nparts += fgrid;
+  }
+  if (stats)
+    launch_pdl(col_finalize_kernel<0>, dim3(ncols / 4), dim3(kColThreads), 0, s, (const float*)a.partials, nparts,
+               (int)ncols, n_out, eps, momentum, stat, running_mean, running_var, 0, valid_rows);
+  return check_launch("ft3d_conv_os");
+}
+
+}  // extern "C"

@@ -101,6 +101,7 @@ class KernelMap:
         self._event = None
         self._num_pairs = None
         self.aux = {}               # per-map caches owned by the conv kernels (tile schedules, ...)
+        self._os = {}               # side ("out" | "in") -> ops.OsPlan of the output-stationary convolution
 
     @property
     def nbrT(self):
@@ -140,6 +141,33 @@ class KernelMap:
             self._pposT = ops.kmap_pair_positions(self._pairs, self._offsets, self.K, self.nbr.shape[1], 0,
                                                   self.n_in, self.num_pairs())
         return self._pposT
+
+    def os_plan(self, side: str):
+        """Tile schedule of conv_os for the rows of one side of the map: ``"out"`` = the map's output rows (forward
+        conv, dgrad of a transposed conv; table ``nbr``), ``"in"`` = its input rows (dgrad, transposed conv; table
+        ``nbrT``).  A symmetric stride-1 map (nbrT[i,k] == nbr[i,K-1-k]) serves both sides with the "out" schedule
+        and mirrored weights (``kflip``)."""
+        plan = self._os.get(side)
+        if plan is None:
+            table = self.nbr if side == "out" else self.nbrT
+            plan = ops.conv_os_plan(table, self.K, self._num_pairs)
+            self._os[side] = plan
+        return plan
+
+    def os_args(self, role: str):
+        """-> (plan, w_transposed, kflip, n_rows) of a convolution role (forward | dgrad | transposed |
+        dgrad_transposed)."""
+        if role == "forward":
+            return self.os_plan("out"), False, False, self.n_out
+        if role == "dgrad":
+            if self.symmetric:
+                return self.os_plan("out"), True, True, self.n_in
+            return self.os_plan("in"), True, False, self.n_in
+        if role == "transposed":
+            return self.os_plan("in"), False, False, self.n_in
+        if role == "dgrad_transposed":
+            return self.os_plan("out"), True, False, self.n_out
+        raise ValueError(role)
 
     def host_offsets(self):
         self._build_pairs()
@@ -211,6 +239,8 @@ class _SparseConv(torch.autograd.Function):
         if ctx.pairs_path:
             x16 = ops.to_bf16(feats)
             ctx.save_for_backward(x16, kernel)
+            if conv_engine.os_enabled():
+                return conv_engine.os_conv(x16, kmap, kernel, "transposed" if transpose else "forward")[0]
             return conv_engine.pairs_conv(x16, kmap, kernel, role="transposed" if transpose else "forward")
         ctx.save_for_backward(feats, kernel)
         table = kmap.nbrT if transpose else kmap.nbr
@@ -225,7 +255,9 @@ class _SparseConv(torch.autograd.Function):
         gin = gw = None
         if ctx.pairs_path:
             g16 = ops.to_bf16(gout)
-            if ctx.needs_input_grad[0]:
+            if ctx.needs_input_grad[0] and conv_engine.os_enabled():
+                gin = conv_engine.os_conv(g16, kmap, kernel, "dgrad_transposed" if transpose else "dgrad")[0]
+            elif ctx.needs_input_grad[0]:
                 gin = conv_engine.pairs_conv(g16, kmap, kernel, role="dgrad_transposed" if transpose else "dgrad")
             if ctx.needs_input_grad[1]:
                 gw = conv_engine.pairs_wgrad(feats, g16, kmap, kernel.shape[-2], kernel.shape[-1], transpose)

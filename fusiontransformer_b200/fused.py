@@ -82,6 +82,9 @@ class _ConvBNAct(torch.autograd.Function):
                 x16 = ops.to_bf16(feats)
             if kmap is None:                                   # kernel_size 1: dense GEMM, rows are already final
                 y = conv_engine.dense_conv(x16, kernel, w_transposed=False)
+            elif conv_engine.os_enabled():                     # one launch: gather-GEMM, final rows, BN statistics
+                y, stat = conv_engine.os_conv(x16, kmap, kernel, _role(transpose, False),
+                                              bn=(bn.eps, bn.momentum, rm, rv) if training else None)
             else:
                 partial, ppos, ncols = conv_engine.pairs_partial(x16, kmap, kernel, _role(transpose, False))
                 if training:
@@ -145,7 +148,9 @@ class _ConvBNAct(torch.autograd.Function):
                 if need_w:
                     gw = conv_engine.dense_wgrad(saved_in, gy16, cin, cout, into=kernel.grad if sink else None)
             else:
-                if need_in:
+                if need_in and conv_engine.os_enabled():
+                    gin = conv_engine.os_conv(gy16, kmap, kernel, _role(transpose, True))[0]
+                elif need_in:
                     gin = conv_engine.pairs_conv(gy16, kmap, kernel, _role(transpose, True))
                 if need_w and sink is not None and sink.side_wgrad:
                     # gradient goes straight into the arena, nothing downstream in autograd consumes it: run it

@@ -106,7 +106,8 @@ class StaticGeometry:
         self.bidx = slot("bidx", P, (), torch.int32, 0)
         self.labels = slot("labels", P, (), torch.int64, -100)
         self.coord_maps = {s: slot("C%d" % s, self.row_caps[s], (4,), torch.int32, 0) for s in self.strides}
-        self.kernel_maps, self.pair_caps = {}, {}
+        self.kernel_maps, self.pair_caps, self.pass_caps = {}, {}, {}
+        self.use_os = conv_engine.mode() == "tc" and conv_engine.os_enabled()
         for key, km in plan.kernel_maps.items():
             s_in, s_out = self._map_strides(key)
             kpad = km.nbr.shape[1]
@@ -120,8 +121,28 @@ class StaticGeometry:
                 skm._nbrT = slot(key + ".nbrT", self.row_caps[s_in], (kpad,), torch.int32, -1)
             skm._pairs = slot(key + ".pairs", lcap, (2,), torch.int32, 0)
             skm._offsets = slot(key + ".offsets", km.K + 1, (), torch.int32, 0)
-            skm._ppos = slot(key + ".ppos", self.row_caps[s_out], (kpad,), torch.int32, -1)
-            skm._pposT = slot(key + ".pposT", self.row_caps[s_in], (kpad,), torch.int32, -1)
+            if self.use_os:
+                # tile schedules of the output-stationary convolution, padded with empty tiles / passes
+                for side, op in km._os.items():
+                    rows = self.row_caps[s_out] if side == "out" else self.row_caps[s_in]
+                    tcap = (rows + 127) // 128
+                    name = "%s.os_%s" % (key, side)
+                    n_pass, n_unit, n_slot = op.host_counts()[:3]
+                    old = prev.pass_caps.get(name, (0, 0, 0)) if prev is not None else (0, 0, 0)
+                    pcap, ucap, scap = (max(int(n_pass * 1.25) + 8, old[0]), max(int(n_unit * 1.25) + 8, tcap, old[1]),
+                                        max(int(n_slot * 1.5) + 8, old[2]))
+                    self.pass_caps[name] = (pcap, ucap, scap)
+                    # `num` carries the batch's real unit count: the kernel never walks the padding units
+                    skm._os[side] = ops.OsPlan(slot(name + ".units", ucap, (8,), torch.int32, 0),
+                                               slot(name + ".split", tcap, (4,), torch.int32, 0),
+                                               slot(name + ".num", 8, (), torch.int32, 0),
+                                               slot(name + ".out_row", tcap * 128, (), torch.int32, -1),
+                                               slot(name + ".pass_k", pcap, (), torch.int32, 0),
+                                               slot(name + ".pass_idx", pcap, (128,), torch.int32, -1),
+                                               rows, km.K, counts=(pcap, ucap, scap, 0, 0))
+            else:
+                skm._ppos = slot(key + ".ppos", self.row_caps[s_out], (kpad,), torch.int32, -1)
+                skm._pposT = slot(key + ".pposT", self.row_caps[s_in], (kpad,), torch.int32, -1)
             skm._num_pairs = lcap                        # sizes the grids and the partial-row buffers
             self.kernel_maps[key] = skm
         self.p2v = {s: (slot("p2v%d.idx" % s, P, (), torch.int32, -1),
@@ -154,7 +175,18 @@ class StaticGeometry:
             return False
         if any(plan.coord_maps[s].shape[0] > self.row_caps[s] for s in self.strides):
             return False
-        return all(km.num_pairs() <= self.pair_caps[k] for k, km in plan.kernel_maps.items())
+        for key, km in plan.kernel_maps.items():
+            if km.num_pairs() > self.pair_caps[key]:
+                return False
+            if self.use_os:
+                if set(km._os) != set(self.kernel_maps[key]._os):
+                    return False
+                for side, op in km._os.items():
+                    n_pass, n_unit, n_slot = op.host_counts()[:3]
+                    pcap, ucap, scap = self.pass_caps["%s.os_%s" % (key, side)]
+                    if n_pass > pcap or n_unit > ucap or n_slot > scap:
+                        return False
+        return True
 
     def load(self, plan: GeometryPlan):
         """Copy one batch's geometry and inputs into the static buffers (enqueued on the current stream)."""
@@ -178,8 +210,19 @@ class StaticGeometry:
                 S[key + ".nbrT"].load(km.nbrT, copies, fills)
             S[key + ".pairs"].load(km.pairs_padded[:L], copies, fills)
             S[key + ".offsets"].load(km.pair_offsets, copies, fills)
-            S[key + ".ppos"].load(km.ppos, copies, fills)
-            S[key + ".pposT"].load(km.pposT, copies, fills)
+            if self.use_os:
+                for side, op in km._os.items():
+                    name = "%s.os_%s" % (key, side)
+                    n_pass, n_unit = op.host_counts()[:2]
+                    S[name + ".units"].load(op.units[:n_unit], copies, fills)
+                    S[name + ".split"].load(op.split_tiles[:max(op.host_counts()[4], 1)], copies, fills)
+                    S[name + ".num"].load(op.num, copies, fills)
+                    S[name + ".out_row"].load(op.out_row, copies, fills)
+                    S[name + ".pass_k"].load(op.pass_k[:n_pass], copies, fills)
+                    S[name + ".pass_idx"].load(op.pass_idx[:n_pass], copies, fills)
+            else:
+                S[key + ".ppos"].load(km.ppos, copies, fills)
+                S[key + ".pposT"].load(km.pposT, copies, fills)
         for s, (idx, cnt) in plan.p2v.items():
             S["p2v%d.idx" % s].load(idx, copies, fills)
             S["p2v%d.cnt" % s].load(cnt, copies, fills)
@@ -243,7 +286,7 @@ class GraphedStep:
         if self.static is not None:                          # keep only the numbers: the old buffers are freed first
             import types
             prev = types.SimpleNamespace(n_points_cap=self.static.n_points_cap, row_caps=dict(self.static.row_caps),
-                                         pair_caps=dict(self.static.pair_caps))
+                                         pair_caps=dict(self.static.pair_caps), pass_caps=dict(self.static.pass_caps))
         self.static = None
         self.static = StaticGeometry(plan, self.slack, prev=prev)
         self.static.load(plan)

@@ -448,6 +448,116 @@ def conv_reduce(partial, ppos, ncols):
     return out
 
 
+# ----------------------------------------------------------------------------- output-stationary tensor-core path
+OS_CHUNK_PASSES = 0     # passes per work unit of conv_os; 0 = chosen per schedule (csrc/os_plan.cu)
+
+
+class OsPlan:
+    """Schedule of one side of a kernel map for ``conv_os`` (csrc/os_plan.cu): 128-row tiles of output rows sorted by
+    occupancy mask, the offsets ("passes") each tile visits with their gather indices, and the work units (tiles, or
+    pass ranges of heavy tiles) in longest-first order."""
+
+    __slots__ = ("units", "split_tiles", "num", "out_row", "pass_k", "pass_idx", "T", "n_rows", "K", "counts")
+
+    def __init__(self, units, split_tiles, num, out_row, pass_k, pass_idx, n_rows, K, counts=None):
+        self.units, self.split_tiles, self.num = units, split_tiles, num
+        self.out_row, self.pass_k, self.pass_idx = out_row, pass_k, pass_idx
+        self.T, self.n_rows, self.K = out_row.shape[0] // 128, n_rows, K
+        self.counts = counts            # host copy of num[:5] = (passes, units, scratch slots, cap, split tiles)
+
+    def host_counts(self):
+        """(passes, units, scratch slots, cap, split tiles) on the host (one read, cached); validates the allocation."""
+        if self.counts is None:
+            self.counts = tuple(int(v) for v in self.num.tolist()[:5])
+        P, U = self.counts[0], self.counts[1]
+        if P > self.pass_k.shape[0] or U > self.units.shape[0]:
+            raise Ft3dError("conv_os schedule: %d passes / %d units exceed the allocation (%d / %d)"
+                            % (P, U, self.pass_k.shape[0], self.units.shape[0]))
+        return self.counts
+
+    def passes(self) -> int:
+        return self.host_counts()[0]
+
+    def scratch_slots(self) -> int:
+        return self.host_counts()[2]
+
+    def tensors(self):
+        return [self.units, self.split_tiles, self.num, self.out_row, self.pass_k, self.pass_idx]
+
+
+def conv_os_plan(table: torch.Tensor, k: int, max_pairs: int | None = None) -> OsPlan:
+    """``table`` int32 [n_rows, kpad]: the neighbour table seen from the rows the convolution PRODUCES."""
+    table = _chk(table, torch.int32, "table")
+    n_rows, kpad = table.shape
+    dev = table.device
+    T = (n_rows + 127) // 128
+    cap = max(T * k, 1)
+    if max_pairs is not None:
+        cap = max(min(cap, int(max_pairs)), 1)         # every pass holds at least one pair
+    chunk = int(OS_CHUNK_PASSES)
+    ucap = 4 * T                                       # a tile is split into at most 4 units
+    units = torch.empty((ucap, 8), dtype=torch.int32, device=dev)
+    split_tiles = torch.empty((max(T, 1), 4), dtype=torch.int32, device=dev)
+    out_row = torch.empty(T * 128, dtype=torch.int32, device=dev)
+    pass_k = torch.empty(cap, dtype=torch.int32, device=dev)
+    pass_idx = torch.empty((cap, 128), dtype=torch.int32, device=dev)
+    num = torch.empty(8, dtype=torch.int32, device=dev)
+    ws = _ws(lib().conv_os_plan_workspace(n_rows, ucap), dev)
+    lib().conv_os_plan(table.data_ptr(), n_rows, k, kpad, cap, ucap, chunk, units.data_ptr(), split_tiles.data_ptr(),
+                       out_row.data_ptr(), pass_k.data_ptr(), pass_idx.data_ptr(), num.data_ptr(), ws.data_ptr(),
+                       ws.numel(), _stream())
+    return OsPlan(units, split_tiles, num, out_row, pass_k, pass_idx, n_rows, k)
+
+
+_OS_SCRATCH = {}
+
+
+def os_scratch(device, nbytes: int):
+    """Per-CTA statistics rows + partial tiles of split tiles for conv_os; one buffer per (device, stream) -- the
+    launches of a stream are ordered, so every layer can share it -- grown on demand."""
+    key = (device.index, _stream())
+    hit = _OS_SCRATCH.get(key)
+    if hit is None or hit.numel() < nbytes:
+        hit = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
+        _OS_SCRATCH[key] = hit
+    return hit
+
+
+OS_TRACE = None      # when a list: conv_os appends (tag, per-CTA trace tensor [grid,8] int64); tools/conv_os_probe.py
+
+
+def conv_os(x16, plan: OsPlan, w, w_transposed: bool, kflip: bool, n_out: int, owner=None, bn=None,
+            scratch_slots: int | None = None):
+    """Output-stationary tcgen05 convolution.  ``bn`` = (eps, momentum, running_mean, running_var) adds the
+    BatchNorm training statistics of the result: returns (y [n_out,ncols] f32, stat [2,ncols] f32 or None)."""
+    x16 = _chk(x16, torch.bfloat16, "x16")
+    cin, cout = w.shape[-2], w.shape[-1]
+    red, ncols = (cout, cin) if w_transposed else (cin, cout)
+    if x16.shape[1] != red:
+        raise Ft3dError("conv: feature width %d != %d" % (x16.shape[1], red))
+    img = packed_weights(w, w_transposed, owner)
+    dev = x16.device
+    out = torch.empty((n_out, ncols), dtype=torch.float32, device=dev)
+    stat = None
+    eps = momentum = 0.0
+    rm = rv = None
+    if bn is not None:
+        eps, momentum, rm, rv = bn
+        stat = torch.empty((2, ncols), dtype=torch.float32, device=dev)
+    slots = plan.scratch_slots() if scratch_slots is None else scratch_slots
+    ws = os_scratch(dev, lib().conv_os_workspace(ncols, slots))
+    trace = None
+    if OS_TRACE is not None:
+        trace = torch.zeros((min(plan.T, 148), 8), dtype=torch.int64, device=dev)
+        OS_TRACE.append(trace)
+    lib().conv_os(x16.data_ptr(), x16.shape[0], plan.units.data_ptr(), plan.split_tiles.data_ptr(),
+                  plan.num.data_ptr(), plan.out_row.data_ptr(),
+                  plan.pass_k.data_ptr(), plan.pass_idx.data_ptr(), plan.units.shape[0], plan.T, slots, plan.K,
+                  int(kflip), red, ncols, img.data_ptr(), out.data_ptr(), n_out, _valid(n_out), float(eps),
+                  float(momentum), _p(stat), _p(rm), _p(rv), ws.data_ptr(), ws.numel(), _p(trace), _stream())
+    return out, stat
+
+
 # ----------------------------------------------------------------------------- fused BatchNorm / ReLU / residual
 # Static-shape execution (graph.py): activations are padded to a capacity; the number of real rows of every padded
 # row dimension lives in a device int32 and is looked up here by that dimension (capacities are made distinct).

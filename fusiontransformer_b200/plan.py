@@ -46,6 +46,8 @@ class GeometryPlan:
             out += [t.keys, t.vals]
         for km in self.kernel_maps.values():
             out += [km.nbr, km._nbrT, km._pairs, km._offsets, km._ppos, km._pposT]
+            for op in km._os.values():
+                out += op.tensors()
         for a, b in list(self.p2v.values()) + list(self.v2p.values()):
             out += [a, b]
         for v in self.extras.values():
@@ -61,8 +63,14 @@ class GeometryPlan:
 
 
 def _force(km: KernelMap, need_nbrT: bool):
+    from . import conv_engine
     km.num_pairs()              # pairs, offsets, ppos + the single host read of this map
-    km.pposT
+    if conv_engine.mode() == "tc" and conv_engine.os_enabled():
+        km.os_plan("out")       # tile schedules of the output-stationary convolution (forward / dgrad sides)
+        if not km.symmetric:
+            km.os_plan("in")
+    else:
+        km.pposT
     if need_nbrT:
         km.nbrT
 
@@ -94,6 +102,12 @@ def build_plan(coords: torch.Tensor, strides=(1, 2, 4, 8, 16), v2p_strides=(1, 1
         plan.coord_maps[nxt] = cn
         plan.tables[nxt] = CoordTable.from_coords(cn)
         c, s = cn, nxt
+    os_plans = [op for km in plan.kernel_maps.values() for op in km._os.values()]
+    if os_plans:                # one host read for the (passes, units, scratch slots, cap) of every schedule
+        nums = torch.stack([op.num for op in os_plans]).tolist()
+        for op, n in zip(os_plans, nums):
+            op.counts = tuple(int(v) for v in n)
+            op.host_counts()
     for s in v2p_strides:
         plan.v2p[s] = ops.v2p_build(zc, s, plan.tables[s])
     for s in p2v_strides:

@@ -100,3 +100,13 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def reorder_bits(m, rare_msb=True):
+    """Permute mask bits so that the rarest offsets become the most significant sort digits."""
+    freq = np.array([((m >> k) & 1).sum() for k in range(27)])
+    order = np.argsort(freq if not rare_msb else -freq, kind="stable")   # order[0] -> bit 0 (LSB)
+    out = np.zeros_like(m)
+    for newbit, k in enumerate(order):
+        out |= ((m >> k) & 1) << newbit
+    return out
