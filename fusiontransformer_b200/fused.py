@@ -82,7 +82,7 @@ class _ConvBNAct(torch.autograd.Function):
                 x16 = ops.to_bf16(feats)
             if kmap is None:                                   # kernel_size 1: dense GEMM, rows are already final
                 y = conv_engine.dense_conv(x16, kernel, w_transposed=False)
-            elif conv_engine.os_enabled():                     # one launch: gather-GEMM, final rows, BN statistics
+            elif conv_engine.os_enabled():                     # gather-GEMM, final rows and the BN statistics
                 y, stat = conv_engine.os_conv(x16, kmap, kernel, _role(transpose, False),
                                               bn=(bn.eps, bn.momentum, rm, rv) if training else None)
             else:
@@ -129,12 +129,12 @@ class _ConvBNAct(torch.autograd.Function):
         sink = getattr(kernel, "_ft3d_sink", None)
         if sink is not None and not (sink.owns(kernel) and sink.owns(gamma) and sink.owns(beta)):
             sink = None
+        need_in, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        want_res = ctx.has_res and ctx.needs_input_grad[4] and mask is not None
         if sink is not None:
             red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat, gamma.grad, beta.grad)
         else:
             red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat)
-        need_in, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        want_res = ctx.has_res and ctx.needs_input_grad[4] and mask is not None
         gy, gy16, gres = ops.bn_bwd_apply(gz, y, m16, m32, stat, gamma, red if ctx.training else None,
                                           want_f32=not tc, want_bf16=tc, want_res=want_res)
         if ctx.has_res and ctx.needs_input_grad[4] and mask is None:
@@ -187,6 +187,27 @@ class _ConvBNAct(torch.autograd.Function):
         return gin, gw, dgamma, dbeta, gres, None, None, None, None, None
 
 
+def _bn_forward(y, bn, training, rm, rv, gamma, beta, relu):
+    """BatchNorm(+ReLU) of a plain fp32 [N,C] tensor -> (z, stat)."""
+    if training:
+        stat = ops.bn_stats(y, bn.eps, bn.momentum, rm, rv)
+    else:
+        stat = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)]).contiguous()
+    z, _ = ops.bn_apply(y, stat, gamma, beta, None, relu, want_f32=True, want_bf16=False)
+    return z, stat
+
+
+def _bn_backward(gz, y, mask, stat, gamma, beta, sink, training, want_bf16, want_f32=True):
+    """-> (gy f32 | None, gy16 | None, dgamma, dbeta); with a gradient arena the parameter gradients are added in place."""
+    if sink is not None:
+        red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat, gamma.grad, beta.grad)
+    else:
+        red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat)
+    gy, gy16, _ = ops.bn_bwd_apply(gz, y, None, mask, stat, gamma, red if training else None, want_f32=want_f32,
+                                   want_bf16=want_bf16, want_res=False)
+    return gy, gy16, dgamma, dbeta
+
+
 class _BNAct(torch.autograd.Function):
     """``relu?(batch_norm(y))`` on a plain [N,C] tensor: the point-branch ``Linear -> BatchNorm1d -> ReLU`` blocks
     (models/spvcnn.py:164-180, middle_fusion.py:18-22) on the same kernels as the voxel branch."""
@@ -196,11 +217,7 @@ class _BNAct(torch.autograd.Function):
         training = bn.training or bn.running_mean is None
         rm, rv = (bn.running_mean, bn.running_var) if (bn.training and bn.track_running_stats) else (None, None)
         y = y.contiguous()
-        if training:
-            stat = ops.bn_stats(y, bn.eps, bn.momentum, rm, rv)
-        else:
-            stat = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)]).contiguous()
-        z, _ = ops.bn_apply(y, stat, gamma, beta, None, relu, want_f32=True, want_bf16=False)
+        z, stat = _bn_forward(y, bn, training, rm, rv, gamma, beta, relu)
         ctx.training, ctx.beta = training, beta
         ctx.save_for_backward(y, gamma, stat, z if relu else None)
         return z
@@ -213,14 +230,10 @@ class _BNAct(torch.autograd.Function):
         sink = getattr(gamma, "_ft3d_sink", None)
         if sink is not None and not (sink.owns(gamma) and sink.owns(beta)):
             sink = None
+        gy, _, dgamma, dbeta = _bn_backward(gz, y, mask, stat, gamma, beta, sink, ctx.training, want_bf16=False)
         if sink is not None:
-            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat, gamma.grad, beta.grad)
             sink.note(gamma)
             sink.note(beta)
-        else:
-            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat)
-        gy, _, _ = ops.bn_bwd_apply(gz, y, None, mask, stat, gamma, red if ctx.training else None,
-                                    want_f32=True, want_bf16=False, want_res=False)
         return gy, dgamma, dbeta, None, None
 
 
@@ -236,14 +249,18 @@ class _LinearBNAct(torch.autograd.Function):
         training = bn.training or bn.running_mean is None
         rm, rv = (bn.running_mean, bn.running_var) if (bn.training and bn.track_running_stats) else (None, None)
         x = x.contiguous()
-        y = torch.addmm(bias, x, weight.t()) if bias is not None else x.matmul(weight.t())
-        if training:
-            stat = ops.bn_stats(y, bn.eps, bn.momentum, rm, rv)
+        out_f, in_f = weight.shape
+        tc = conv_engine.pairs_ok(in_f, out_f)
+        if tc:       # a14 on the tcgen05 kernels: identity-gather GEMM, bf16 operands, fp32 accumulation
+            x = ops.to_bf16(x)
+            y = ops.conv_pairs_tc(x, None, None, 1, 0, x.shape[0], weight.detach().unsqueeze(0), True, owner=weight)
+            if bias is not None:
+                y += bias
         else:
-            stat = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)]).contiguous()
-        z, _ = ops.bn_apply(y, stat, gamma, beta, None, relu, want_f32=True, want_bf16=False)
-        ctx.training, ctx.beta, ctx.bias = training, beta, bias
-        ctx.save_for_backward(x, weight, y, gamma, stat, z if relu else None)
+            y = torch.addmm(bias, x, weight.t()) if bias is not None else x.matmul(weight.t())
+        z, stat = _bn_forward(y, bn, training, rm, rv, gamma, beta, relu)
+        ctx.training, ctx.beta, ctx.bias, ctx.tc = training, beta, bias, tc
+        ctx.save_for_backward(x, weight, y, gamma, stat, z if relu else None)      # tc: x is the bf16 copy
         return z
 
     @staticmethod
@@ -256,26 +273,27 @@ class _LinearBNAct(torch.autograd.Function):
         if sink is not None and not (sink.owns(weight) and sink.owns(gamma) and sink.owns(beta)
                                      and (bias is None or sink.owns(bias))):
             sink = None
-        if sink is not None:
-            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat, gamma.grad, beta.grad)
-        else:
-            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, None, mask, stat)
-        tc = (conv_engine.mode() == "tc" and out_f % 16 == 0 and out_f <= 512 and in_f % 32 == 0 and in_f <= 256
-              and ctx.needs_input_grad[1])
-        gy, gy16, _ = ops.bn_bwd_apply(gz, y, None, mask, stat, gamma, red if ctx.training else None,
-                                       want_f32=True, want_bf16=tc, want_res=False)
-        gx = gy.matmul(weight) if ctx.needs_input_grad[0] else None
-        gw = gb = None
+        tc = ctx.tc
+        want_gb = bias is not None and ctx.needs_input_grad[2]
+        gy, gy16, dgamma, dbeta = _bn_backward(gz, y, mask, stat, gamma, beta, sink, ctx.training, want_bf16=tc,
+                                               want_f32=(not tc) or want_gb)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if tc:       # gX = gy W : the same identity-gather GEMM with the untransposed image
+                gx = ops.conv_pairs_tc(gy16, None, None, 1, 0, gy16.shape[0], weight.detach().unsqueeze(0), False,
+                                       owner=weight)
+            else:
+                gx = gy.matmul(weight)
         if ctx.needs_input_grad[1]:
             if tc:       # gW[out,in] = gy^T x : the wgrad kernel with (a, b) = (gy, x) and an identity pair list
-                gw = ops.conv_wgrad_pairs_tc(gy16, ops.to_bf16(x), None, None, 1, 0, out_f, in_f, x.shape[0],
+                gw = ops.conv_wgrad_pairs_tc(gy16, x, None, None, 1, 0, out_f, in_f, x.shape[0],
                                              into=weight.grad.view(1, out_f, in_f) if sink is not None else None)
                 gw = None if sink is not None else gw.view(out_f, in_f)
             elif sink is not None:
                 weight.grad.addmm_(gy.t(), x)
             else:
                 gw = gy.t().matmul(x)
-        if bias is not None and ctx.needs_input_grad[2]:
+        if want_gb:
             gb = ops.col_sum(gy, into=bias.grad if sink is not None else None)
             if sink is not None:
                 gb = None
@@ -386,6 +404,9 @@ def weight_packer(model: nn.Module):
     optimizer update) instead of one pack launch per layer and orientation."""
     ks = [m.kernel for m in model.modules() if isinstance(m, spnn.Conv3d)
           and conv_engine.pairs_ok(m.kernel.shape[-2], m.kernel.shape[-1])]
+    # nn.Linear weights [out,in] of the point-branch / fusion MLPs (a14), read as a [1, out, in] kernel
+    ks += [m.weight for m in model.modules() if type(m) is nn.Linear
+           and conv_engine.pairs_ok(m.out_features, m.in_features)]
     return ops.WeightPacker(ks)
 
 

@@ -350,6 +350,7 @@ class GraphedStep:
             self.static.load(plan)
         self.graph.replay()
         self.replays += 1
+        ops.REPLAY_EPOCH += 1        # the replayed optimizer step moved the weights: cached bf16 images are stale
         for b in self._bns:
             b._ft3d_pending_batches = getattr(b, "_ft3d_pending_batches", 0) + 1
         if self.after_replay is not None:

@@ -329,6 +329,8 @@ def conv_wgrad_f32(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
 _PACK_CACHE = {}
 FORCE_REPACK = False     # graph.py sets this while capturing: the pack launch must be part of every replay
 PACK_EPOCH = 0           # bumped per capture; images packed by pack_all() inside the capture are not packed twice
+REPLAY_EPOCH = 0         # bumped by graph.GraphedStep after every replay: the captured optimizer step moved the weights
+                         # on the device without touching Tensor._version, so every cached image is one step old
 
 
 class WeightPacker:
@@ -366,7 +368,7 @@ class WeightPacker:
         for ref, wt, ptr, img in self.entries:
             p = ref()
             if p is not None:
-                _PACK_CACHE[(id(p), wt)] = (ref, p._version, ptr, img, PACK_EPOCH)
+                _PACK_CACHE[(id(p), wt)] = (ref, p._version, ptr, img, PACK_EPOCH, REPLAY_EPOCH)
 
 
 def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Tensor:
@@ -379,7 +381,7 @@ def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Ten
     key = (id(owner), bool(w_transposed))
     hit = _PACK_CACHE.get(key)
     if (hit is not None and hit[0]() is owner and hit[1] == owner._version and hit[2] == w.data_ptr()
-            and (not FORCE_REPACK or (len(hit) > 4 and hit[4] == PACK_EPOCH))):
+            and hit[5] == REPLAY_EPOCH and (not FORCE_REPACK or hit[4] == PACK_EPOCH)):
         return hit[3]
     k, cin, cout = w.shape
     red, ncols = (cout, cin) if w_transposed else (cin, cout)
@@ -390,7 +392,7 @@ def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Ten
     if len(_PACK_CACHE) > 512:
         for kk in [kk for kk, v in _PACK_CACHE.items() if v[0]() is None]:
             del _PACK_CACHE[kk]
-    _PACK_CACHE[key] = (weakref.ref(owner), owner._version, w.data_ptr(), img, -1)
+    _PACK_CACHE[key] = (weakref.ref(owner), owner._version, w.data_ptr(), img, -1, REPLAY_EPOCH)
     return img
 
 

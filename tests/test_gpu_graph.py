@@ -108,3 +108,34 @@ def test_graph_recaptures_when_a_batch_does_not_fit(monkeypatch):
         loss = gs.step(dataflow.prepare_batch(hb, "cuda")).item()
         assert np.isfinite(loss)
     assert gs.captures >= 2
+
+
+def test_eval_between_replays_sees_the_updated_weights(monkeypatch):
+    """train(replay) -> eval -> train(replay) -> eval: the optimizer step inside a replay moves the weights on the
+    device without bumping Tensor._version, so the cached bf16 weight images must be invalidated by the replay itself
+    (ops.REPLAY_EPOCH); every eval must equal one run with freshly packed images."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import dataflow, ops
+    from fusiontransformer_b200.graph import GraphedStep
+    monkeypatch.setenv("FT3D_CONV", "tc")
+    hb = _host_batches()[0]
+    net, body = _trainer("tc")
+    gs = GraphedStep(body, modules=[net])
+
+    def evaluate():
+        plan = dataflow.prepare_batch(hb, "cuda")
+        net.eval()
+        with torch.no_grad():
+            out = net(plan.extras["lidar"], torch.zeros(plan.extras["lidar"].C.shape[0], 96, device="cuda"), plan=plan)
+        net.train()
+        return out["lidar_seg_logit"].clone()
+
+    for _ in range(2):
+        gs.step(dataflow.prepare_batch(hb, "cuda"))
+    for _ in range(2):
+        gs.step(dataflow.prepare_batch(hb, "cuda"))        # a replay: weights move, _version does not
+        got = evaluate()
+        ops._PACK_CACHE.clear()                              # force fresh images
+        want = evaluate()
+        # (the point->voxel scatter sums with fp32 atomics: equal up to summation order; a stale image differs by ~1e-2)
+        assert ((got - want).norm() / want.norm()).item() < 1e-3
