@@ -40,6 +40,7 @@ class GradSync:
                 bstart, bidx = off, bidx + 1
         if off > bstart:
             self.buckets.append((bstart, off))
+        self._view = {p: p.grad for p in order}      # the arena view of every parameter (re-adopted if `.grad` is replaced)
         self._need = [0] * len(self.buckets)
         for p in order:
             self._need[self._bucket_of[p]] += 1
@@ -61,6 +62,20 @@ class GradSync:
         g = p.grad
         return g is not None and g.untyped_storage().data_ptr() == self.flat.untyped_storage().data_ptr()
 
+    def _adopt(self, p):
+        """``optimizer.zero_grad()`` (set_to_none=True, what the reference's train_step calls) drops the arena views:
+        the fused kernels then return fresh gradient tensors and autograd installs them as ``.grad``.  Bring such a
+        gradient back into the arena (copy + re-bind the view) so that the exchange reduces what backward produced."""
+        if self.owns(p):
+            return
+        view = self._view[p]
+        g = p.grad
+        if g is None:
+            view.zero_()                 # an unused parameter contributes zeros (find_unused_parameters=True)
+        else:
+            view.copy_(g)
+            p.grad = view
+
     def note(self, p):
         """A kernel has added p's gradient into the arena (no autograd accumulation => no hook fires)."""
         if self.world > 1:
@@ -79,6 +94,11 @@ class GradSync:
             dist.broadcast(t.data, 0, group=self.group)
 
     def zero_grad(self):
+        """Use instead of ``optimizer.zero_grad()``: zeroes the arena in one launch and keeps the ``.grad`` views (an
+        ``optimizer.zero_grad()`` is tolerated -- see ``_adopt`` -- at the price of one copy per parameter)."""
+        for p in self.params:
+            if p.grad is not self._view[p]:
+                p.grad = self._view[p]
         self.flat.zero_()
         self._seen = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
@@ -101,6 +121,7 @@ class GradSync:
     def _hook(self, p):
         if self.deferred:
             return
+        self._adopt(p)
         b = self._bucket_of[p]
         self._seen[b] += 1
         if self._seen[b] == self._need[b]:
@@ -109,6 +130,11 @@ class GradSync:
     def finish(self):
         """Call after backward: launches buckets with unused parameters, waits, and averages over ranks."""
         self._join_side()
+        for b, launched in enumerate(self._launched):
+            if not launched:             # parameters whose gradient never arrived through a hook (unused, or world 1)
+                for p in self.params:
+                    if self._bucket_of[p] == b:
+                        self._adopt(p)
         if self.world == 1:
             return
         if self.deferred:
@@ -124,6 +150,10 @@ class GradSync:
         self._works = []
         if not self._avg:
             self.flat.mul_(1.0 / self.world)
+        # re-arm for the next step here, not only in zero_grad(): a caller that clears gradients with
+        # optimizer.zero_grad() (or a graph replay, which runs no Python) never reaches GradSync.zero_grad()
+        self._seen = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
 
 
 def shard_indices(num_items: int, rank: int, world: int, epoch: int = 0, shuffle: bool = False, seed: int = 0):

@@ -84,6 +84,63 @@ def test_gradsync_world2_matches_full_batch():
         assert torch.allclose(got, want, atol=1e-6)
 
 
+def _worker_optimizer_zero_grad(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fusiontransformer_b200.dp import GradSync, shard_indices
+    torch.manual_seed(5)
+    net = Net()
+    sync = GradSync(net, bucket_bytes=256)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(8, 8, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    idx = shard_indices(8, rank, world)
+    out = []
+    for step in range(2):
+        opt.zero_grad()                          # set_to_none=True: the arena views are gone
+        (((net(x[idx]) - y[idx]) ** 2).sum() / 8 * world).backward()
+        sync.finish()
+        out.append([None if p.grad is None else p.grad.clone().numpy() for p in net.parameters()])
+        opt.step()
+    q.put((rank, out, [p.data.clone().numpy() for p in net.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_optimizer_zero_grad_does_not_break_the_exchange():
+    """``optimizer.zero_grad()`` sets the gradients to None; the exchange must still reduce what backward
+    produced (not a stale arena) and leave every rank with the same averaged gradient and the same weights."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_optimizer_zero_grad, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, g0, w0), (_, g1, w1) = res
+    for step in range(2):
+        for a, b in zip(g0[step], g1[step]):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert torch.allclose(torch.from_numpy(a), torch.from_numpy(b))
+    for a, b in zip(w0, w1):
+        assert torch.allclose(torch.from_numpy(a), torch.from_numpy(b))     # the replicas did not diverge
+    # step 0 gradient == gradient of the full batch on one process
+    torch.manual_seed(5)
+    net = Net()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(8, 8, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    (((net(x) - y) ** 2).sum() / 8).backward()
+    for p, got in zip(net.parameters(), g0[0]):
+        if p.grad is not None:
+            assert torch.allclose(torch.from_numpy(got), p.grad, atol=1e-6)
+
+
 def _worker_deferred(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
