@@ -119,7 +119,7 @@ LAUNCHES = {
     "conv_pack_weights": 1, "conv_gather_tc": 1, "conv_wgrad_tc": 1, "to_bf16": 1, "conv_pairs_tc": 1,
     "conv_reduce": 1, "conv_wgrad_pairs_tc": 1, "kmap_pair_positions": 3, "conv_reduce_bn": 2, "bn_stats": 2,
     "bn_apply": 1, "col_sum": 2, "seg_loss": 3, "confusion_update": 1, "bn_bwd_reduce": 2, "conv_pack_weights_multi": 1, "bn_bwd_apply": 1,
-    "conv_os": 3, "conv_os_plan": 13,
+    "conv_os": 3, "conv_os_plan": 13, "conv_wgrad_pairs_tc_det": 2,
 }
 
 

@@ -706,14 +706,81 @@ conv_wgrad_pairs_tc_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
-// ------------------------------------------------------------------------------------------------ persistent wgrad
-// Same arithmetic as conv_wgrad_pairs_tc_kernel, organised like the persistent forward kernel: a CTA owns a contiguous
-// run of units (unit = one 128-pair tile x one 128-wide Cin block, Cin-block-major so that consecutive units share
-// their (offset, Cin block) accumulator), streams the gathered A/G stages through a ring that runs across unit
-// boundaries, keeps the running sum in one of TWO TMEM accumulators and flushes it (red.global.add.v4.f32 through a
-// per-warp staging transpose => full 128-byte segments) only when the (offset, Cin block) changes, while the gathers
-// and MMAs of the next group proceed.  Warp roles (320 threads):
-//   0-3  gather producers   4  idle   5  MMA issuer   6-9  flush (TMEM quadrant = warp % 4)
+// The unit line [0, U) of the persistent wgrad kernel (unit u = Cin block u / T, tile u % T) is cut at the CTA run
+// boundaries (multiples of `chunk`) and at the starts of the non-empty (Cin block, offset) groups; the pieces between
+// cuts are the SEGMENTS, each flushed exactly once.  Index of the segment that starts at unit `pos` = number of
+// distinct cut positions in (0, pos].  `off` = the K+1 pair prefix offsets (shared-memory copy).
+__device__ __forceinline__ int wg_segment_index(const int32_t* off, int K, int T, int MB, int chunk, int pos) {
+  int n = pos / chunk;
+  for (int mb = 0; mb < MB; ++mb) {
+    int tp = 0;
+    for (int k = 0; k < K; ++k) {
+      const int nt = (off[k + 1] - off[k] + kTileRows - 1) / kTileRows;
+      if (nt > 0) {
+        const int p = mb * T + tp;
+        if (p > 0 && p <= pos && p % chunk != 0) ++n;      // a group start on a CTA boundary is the same cut
+      }
+      tp += nt;
+    }
+  }
+  return n;
+}
+
+// Second stage of the deterministic persistent weight gradient: gw[k][Cin block rows][:] (+)= sum of the group's
+// segments in unit order.  blockIdx.x = (Cin block, offset), blockIdx.y = row chunk, threadIdx.x = 4 columns.
+__global__ void __launch_bounds__(kColThreads)
+conv_wgrad_fold2_kernel(const float* __restrict__ partial, const int32_t* __restrict__ off_g, int K, int64_t n_identity,
+                        int wgrad_grid, int MB, int cin, int cout, int accumulate, float* __restrict__ gw) {
+  pdl_enter();
+  __shared__ int32_t s_off[40];
+  if (off_g != nullptr) {
+    if ((int)(threadIdx.y * blockDim.x + threadIdx.x) <= K) s_off[threadIdx.y * blockDim.x + threadIdx.x] =
+        __ldg(off_g + threadIdx.y * blockDim.x + threadIdx.x);
+  } else if (threadIdx.x == 0 && threadIdx.y == 0) {
+    s_off[0] = 0;
+    s_off[1] = (int32_t)n_identity;
+  }
+  __syncthreads();
+  const int mb = blockIdx.x / K, k = blockIdx.x % K;
+  int T = 0, tp = 0, nt = 0;
+  for (int j = 0; j < K; ++j) {
+    const int n = (s_off[j + 1] - s_off[j] + kTileRows - 1) / kTileRows;
+    if (j < k) tp += n;
+    if (j == k) nt = n;
+    T += n;
+  }
+  const int m_valid = cin - mb * 128 < 128 ? cin - mb * 128 : 128;
+  const int ch = threadIdx.x * 4;
+  int first = 0, count = 0;
+  if (nt > 0) {
+    const int U = T * MB;
+    const int chunk = (U + wgrad_grid - 1) / wgrad_grid;
+    const int gs = mb * T + tp, ge = gs + nt;
+    first = wg_segment_index(s_off, K, T, MB, chunk, gs);
+    count = 1 + (ge - 1) / chunk - gs / chunk;
+  }
+  const size_t sstride = (size_t)kTileRows * cout;
+  for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < m_valid; r += gridDim.y * blockDim.y) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = partial + ((size_t)first * kTileRows + r) * cout + ch;
+    int i = 0;
+    for (; i + 4 <= count; i += 4) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)i * sstride));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(i + 1) * sstride));
+      const float4 a2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(i + 2) * sstride));
+      const float4 a3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(i + 3) * sstride));
+      add4(acc, a0); add4(acc, a1); add4(acc, a2); add4(acc, a3);
+    }
+    for (; i < count; ++i) add4(acc, __ldg(reinterpret_cast<const float4*>(p + (size_t)i * sstride)));
+    float4* dst = reinterpret_cast<float4*>(gw + ((int64_t)k * cin + mb * 128 + r) * cout + ch);
+    if (accumulate) {
+      const float4 old = *dst;
+      acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+    }
+    *dst = acc;
+  }
+}
+
 constexpr int kWg2MaxSlots = 6;
 
 struct Wg2Header {
@@ -730,7 +797,7 @@ __global__ void __launch_bounds__(kV3Threads)
 conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                               const int2* __restrict__ pairs, const int32_t* __restrict__ off, int K, int ca,
                               int64_t n_identity, int cin, int cout, float* __restrict__ gw, int nslots, int tcols,
-                              int a_blocks) {
+                              int a_blocks, float* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nb_blocks = (cout + 63) / 64;
@@ -875,6 +942,7 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
     const int q = warp & 3;
     float* st = staging + (size_t)(warp - 6) * kV3StageFloats;
     int group = -1, pk = -1, pmb = -1;
+    const int seg0 = partial != nullptr ? wg_segment_index(hdr->off, K, T, MB, chunk, u0) : 0;
     UnitCursor uc;
     uc.seek(hdr->off, K, T, u0);
     for (int u = u0; u <= u1; ++u) {
@@ -891,6 +959,9 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(buf * tcols) + ((uint32_t)(q * 32) << 16);
         const int row0 = pmb * 128 + q * 32;
+        // deterministic mode: this segment (= the part of an (offset, Cin block) group that lies in this CTA's run) owns
+        // slot seg0 + group of `partial`; conv_wgrad_fold2_kernel adds the segments of a group in order
+        float* pslot = partial != nullptr ? partial + ((size_t)(seg0 + group) * kTileRows + q * 32) * cout : nullptr;
         for (int c0 = 0; c0 < cout; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
@@ -904,9 +975,11 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
           for (int i8 = 0; i8 < 8; ++i8) {
             const int r = i8 * 4 + (lane >> 3);
             const int row = row0 + r;
-            if (row < cin)
-              atomicAdd(reinterpret_cast<float4*>(gw + ((int64_t)pk * cin + row) * cout + c0 + (lane & 7) * 4),
-                        *reinterpret_cast<const float4*>(st + r * 36 + (lane & 7) * 4));
+            const float4 val = *reinterpret_cast<const float4*>(st + r * 36 + (lane & 7) * 4);
+            if (pslot != nullptr)
+              *reinterpret_cast<float4*>(pslot + (size_t)r * cout + c0 + (lane & 7) * 4) = val;
+            else if (row < cin)
+              atomicAdd(reinterpret_cast<float4*>(gw + ((int64_t)pk * cin + row) * cout + c0 + (lane & 7) * 4), val);
           }
           __syncwarp();
         }
@@ -1078,6 +1151,81 @@ int ft3d_conv_reduce_bn(const float* partial, const int32_t* ppos, int64_t n_row
                        valid_rows, workspace, workspace_bytes, (cudaStream_t)stream, "ft3d_conv_reduce_bn");
 }
 
+// launch geometry of the persistent wgrad kernel (shared by the atomic and the deterministic entry points)
+struct Wg2Launch {
+  int a_blocks, nslots, tcols, smem_bytes;
+  unsigned grid;
+};
+
+static int wg2_launch(int cin, int cout, int K, int64_t max_pairs, bool has_pairs, Wg2Launch* out) {
+  const int nb_blocks = (cout + 63) / 64;
+  out->a_blocks = cin <= 64 ? 1 : 2;
+  const int stage = (out->a_blocks + nb_blocks) * tc::kBlockBytes;
+  const int fixed = 4 * kV3StageFloats * (int)sizeof(float) + (int)sizeof(Wg2Header) + 1024;
+  out->tcols = tmem_cols_pow2(cout);
+  // two resident CTAs (3-deep rings) when shared memory and TMEM (2 accumulators each) allow, else one CTA
+  int ctas_per_sm = 1, nslots = (226 * 1024 - fixed) / stage;
+  if (fixed + 3 * stage <= 113 * 1024 && 4 * out->tcols <= 512) {
+    ctas_per_sm = 2;
+    nslots = (113 * 1024 - fixed) / stage;
+  }
+  if (nslots > kWg2MaxSlots) nslots = kWg2MaxSlots;
+  if (nslots < 2) return 1;
+  out->nslots = nslots;
+  out->smem_bytes = fixed + nslots * stage;
+  const int64_t tiles = (max_pairs + tc::kTileRows - 1) / tc::kTileRows + (has_pairs ? K : 0);
+  const int64_t units = tiles * ((cin + 127) / 128);
+  const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  out->grid = (unsigned)(units < cap ? units : cap);
+  return 0;
+}
+
+size_t ft3d_conv_wgrad_det_workspace(int32_t K, int32_t cin, int32_t cout, int64_t max_pairs, int32_t has_pairs) {
+  Wg2Launch l;
+  if (wg2_launch(cin, cout, K, max_pairs, has_pairs != 0, &l)) return 0;
+  const size_t slots = (size_t)l.grid + (size_t)K * ((cin + 127) / 128) + 1;
+  return align_up(slots * tc::kTileRows * (size_t)cout * sizeof(float), 256);
+}
+
+int ft3d_conv_wgrad_pairs_tc_det(const void* a_bf16, const void* b_bf16, const int32_t* pairs,
+                                 const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin, int32_t cout,
+                                 int64_t max_pairs, float* gw, int32_t accumulate, void* workspace,
+                                 size_t workspace_bytes, ft3d_stream_t stream) {
+  if (max_pairs == 0) return FT3D_OK;
+  FT3D_REQUIRE(a_bf16 && b_bf16 && gw && K > 0 && K <= 32 && workspace, "ft3d_conv_wgrad_pairs_tc_det: bad arguments");
+  FT3D_REQUIRE((pairs == nullptr) == (pair_offsets == nullptr) && (pairs != nullptr || K == 1),
+               "ft3d_conv_wgrad_pairs_tc_det: identity gather needs K == 1 and no offsets");
+  FT3D_REQUIRE(cin >= 16 && cin % 16 == 0 && cin <= 512 && cout >= 32 && cout % 32 == 0 && cout <= 256,
+               "ft3d_conv_wgrad_pairs_tc_det: unsupported shape cin=%d cout=%d", cin, cout);
+  FT3D_REQUIRE(((uintptr_t)a_bf16 & 15) == 0 && ((uintptr_t)b_bf16 & 15) == 0 && ((uintptr_t)gw & 15) == 0 &&
+                   ((uintptr_t)workspace & 255) == 0,
+               "ft3d_conv_wgrad_pairs_tc_det: pointers must be 16-byte aligned (workspace 256)");
+  FT3D_REQUIRE(workspace_bytes >= ft3d_conv_wgrad_det_workspace(K, cin, cout, max_pairs, pairs != nullptr),
+               "ft3d_conv_wgrad_pairs_tc_det: workspace smaller than ft3d_conv_wgrad_det_workspace(...)");
+  Wg2Launch l;
+  FT3D_REQUIRE(wg2_launch(cin, cout, K, max_pairs, pairs != nullptr, &l) == 0,
+               "ft3d_conv_wgrad_pairs_tc_det: tile does not fit shared memory");
+  static int configured = 0;
+  if (!configured) {
+    FT3D_CUDA(cudaFuncSetAttribute(conv_wgrad_pairs_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 1;
+  }
+  const int MB = (cin + 127) / 128;
+  cudaStream_t s = (cudaStream_t)stream;
+  launch_pdl(conv_wgrad_pairs_tc_v2_kernel, dim3(l.grid), dim3(kV3Threads), l.smem_bytes, s,
+             (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca,
+             max_pairs, cin, cout, gw, l.nslots, l.tcols, l.a_blocks, (float*)workspace);
+  const int cv = cout / 4;
+  int ry = kColThreads / cv;
+  if (ry < 1) ry = 1;
+  if (ry > 32) ry = 32;
+  const int ychunks = (128 + ry - 1) / ry < 4 ? (128 + ry - 1) / ry : 4;
+  launch_pdl(conv_wgrad_fold2_kernel, dim3((unsigned)(K * MB), (unsigned)ychunks), dim3(cv, ry), 0, s,
+             (const float*)workspace, pair_offsets, (int)K, max_pairs, (int)l.grid, MB, (int)cin, (int)cout,
+             (int)accumulate, gw);
+  return check_launch("ft3d_conv_wgrad_pairs_tc_det");
+}
+
 int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32_t* pairs,
                              const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin, int32_t cout,
                              int64_t max_pairs, float* gw, ft3d_stream_t stream) {
@@ -1121,7 +1269,7 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
       const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
       const unsigned grid = (unsigned)(units < cap ? units : cap);
       launch_pdl(conv_wgrad_pairs_tc_v2_kernel, dim3(grid), dim3(kV3Threads), smem_bytes, (cudaStream_t)stream, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs,
-          cin, cout, gw, nslots, tcols, a_blocks);
+          cin, cout, gw, nslots, tcols, a_blocks, (float*)nullptr);
       return check_launch("ft3d_conv_wgrad_pairs_tc");
     }
   }

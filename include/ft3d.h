@@ -250,6 +250,16 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
                  float momentum, float* stat, float* running_mean, float* running_var, void* workspace,
                  size_t workspace_bytes, void* trace, ft3d_stream_t stream);
 
+/* Deterministic weight gradient (two-stage split-K, no atomics): every item of <= 512 pairs of one offset writes its
+ * [128 x cout] block per Cin block into `workspace`, a second launch adds the blocks of each offset in item order and
+ * writes gw (accumulate != 0: adds the sum to what gw holds -- a gradient arena).  Bit-identical from run to run.
+ * workspace: ft3d_conv_wgrad_det_workspace(K, cin, cout, max_pairs, pairs != NULL) bytes, 256-byte aligned. */
+size_t ft3d_conv_wgrad_det_workspace(int32_t K, int32_t cin, int32_t cout, int64_t max_pairs, int32_t has_pairs);
+int ft3d_conv_wgrad_pairs_tc_det(const void* a_bf16, const void* b_bf16, const int32_t* pairs,
+                                 const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin, int32_t cout,
+                                 int64_t max_pairs, float* gw, int32_t accumulate, void* workspace,
+                                 size_t workspace_bytes, ft3d_stream_t stream);
+
 /* ---- a11  spnn.BatchNorm / spnn.ReLU / residual add fused around the convolution
  *          (models/spvcnn.py:26-31,42-47,57-78; torchsparse BatchNorm == nn.BatchNorm1d on .F) ---------------- */
 /* Column reductions are deterministic: per-CTA partial rows in `workspace` (ft3d_bn_workspace(C) bytes), folded in

@@ -235,3 +235,29 @@ def test_conv_os_matches_pair_major_path(ft, geom, monkeypatch):
         x = ft.SparseTensor(feats, geom["C"], 1)
         outs[algo] = ft.nn.functional.conv3d(x, w, 3).F
     assert rel_l2(outs["os"], outs["pairs"]) < 1e-5
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (96, 128), (256, 256), (384, 256)])
+def test_wgrad_two_stage_is_deterministic_and_matches_atomic(ft, geom, monkeypatch, cin, cout):
+    """Two-stage split-K weight gradient: bit-identical across launches, equal to the atomic kernel up to fp32
+    re-association, accumulates into a gradient arena, and handles the dense (identity pair list) case."""
+    from fusiontransformer_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout)
+    km = geom["km3"]
+    n = geom["C"].shape[0]
+    a16 = ops.to_bf16(torch.randn(n, cin, generator=g).cuda())
+    b16 = ops.to_bf16(torch.randn(n, cout, generator=g).cuda())
+    L = km.num_pairs()
+    monkeypatch.setenv("FT3D_WGRAD", "det")
+    outs = [ops.conv_wgrad_pairs_tc(a16, b16, km.pairs_padded, km.pair_offsets, 27, 0, cin, cout, L) for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    arena = torch.ones(27, cin, cout, device="cuda")
+    ops.conv_wgrad_pairs_tc(a16, b16, km.pairs_padded, km.pair_offsets, 27, 0, cin, cout, L, into=arena)
+    assert rel_l2(arena - 1.0, outs[0]) < 1e-6
+    monkeypatch.setenv("FT3D_WGRAD", "atomic")
+    ref = ops.conv_wgrad_pairs_tc(a16, b16, km.pairs_padded, km.pair_offsets, 27, 0, cin, cout, L)
+    assert rel_l2(outs[0], ref) < 1e-5
+    monkeypatch.setenv("FT3D_WGRAD", "det")
+    d0 = ops.conv_wgrad_pairs_tc(a16, b16, None, None, 1, 0, cin, cout, n)
+    want = a16.float().t() @ b16.float()
+    assert rel_l2(d0[0], want) < 1e-5
