@@ -163,6 +163,8 @@ def main():
                          "config) at --gpus > 1; 'stress' = configs[4]")
     ap.add_argument("--batch", type=int, default=0, help="scans per GPU per step (default: the workload's)")
     ap.add_argument("--fusion", default="middle", choices=["none", "middle", "early"])
+    ap.add_argument("--fmap-format", default="channels_last", choices=["channels_last", "nchw"],
+                    help="memory format of the synthetic image-feature map the lift gathers from")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--prefetch-thread", dest="no_prefetch_thread", action="store_false",
@@ -215,7 +217,12 @@ def main():
     host = [dataflow.host_batch_from_scans(s) for s in scans_all]
     resident = [dataflow.to_device(h, dev) for h in host]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    fmap = torch.randn(B, 96, H, W, device=dev, generator=g)   # stands in for the image branch's output (NCHW, fp32)
+    # stands in for the image branch's output [B,96,H,W] fp32 (image_models_billinear.py:111-116).  The producer is
+    # free to choose the memory format: channels-last makes the lift read 384 contiguous bytes per point instead of
+    # 96 sectors (the NCHW map ran the gather at 5 % of the HBM peak); --fmap-format nchw restores the reference layout.
+    fmap = torch.randn(B, 96, H, W, device=dev, generator=g)
+    if args.fmap_format == "channels_last":
+        fmap = fmap.contiguous(memory_format=torch.channels_last)
 
     if conv_engine.mode() == "tc":
         # reduced-precision mode: the point-branch nn.Linear GEMMs (a14, cuBLAS) run on TF32 tensor cores as well
@@ -518,13 +525,17 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if conv_engine.mode() == "tc" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "scans_per_gpu": B, "points_per_batch": nvox, "fusion": args.fusion,
-                       "image_hw": [H, W], "parallelism": "dp%d" % world, "optimizer": "Adam(lr 1e-4, wd 5e-4)",
+                       "image_hw": [H, W], "feature_map_format": args.fmap_format,
+                       "parallelism": "dp%d" % world, "optimizer": "Adam(lr 1e-4, wd 5e-4)",
                        "geometry_prefetch": bool(args.prefetch) and not args.reuse_plans,
                        **({"INVALID_diagnostic": "geometry cached across steps"} if args.reuse_plans else {}),
                        "cuda_graph": ("whole step%s, %d capture(s)" % (
                            "" if world == 1 else (" incl. NCCL exchange" if in_graph else ", exchange after replay"),
                            gstep.captures)) if gstep is not None else "off",
-                       "linear_layers": "cuBLAS TF32" if conv_engine.mode() == "tc" else "cuBLAS fp32",
+                       "linear_layers": ("libft3d tcgen05 (bf16 operands); 96->20 head on cuBLAS" if conv_engine.mode() == "tc"
+                                         else "cuBLAS fp32"),
+                       "conv_algo": os.environ.get("FT3D_CONV_ALGO", "os"),
+                       "wgrad": "two-stage deterministic" if __import__("fusiontransformer_b200.ops", fromlist=["x"]).wgrad_deterministic() else "persistent, fp32 atomics flush",
                        "l2": "no explicit flush: %d distinct batches are cycled and the step's working set (348 MB of "
                              "weights+Adam state, the activations and the %.1f GB feature map) exceeds the 126 MB L2"
                              % (nbatches, B * 96 * H * W * 4 / 1e9)},
@@ -540,11 +551,16 @@ def main():
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        if gstep is not None and in_graph:
+        if gstep is not None and in_graph and os.environ.get("FT3D_NCCL_TEARDOWN", "exit") == "exit":
             # NCCL work captured in CUDA graphs: ProcessGroupNCCL's teardown waited for ever on this stack (torch 2.11,
             # NCCL 2.28) although every collective had completed (the timings above were exchanged and read).  All
-            # results are out; leave without the teardown.
+            # results are out; leave without the teardown.  FT3D_NCCL_TEARDOWN=clean releases the graphs first and
+            # runs the regular teardown.
             os._exit(0)
+        if gstep is not None:
+            gstep.graph = None
+            gstep.static = None
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

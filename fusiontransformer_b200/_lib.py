@@ -116,7 +116,7 @@ LAUNCHES = {
     "gather_rows_i32": 1, "table_build": 2, "table_query": 1, "kmap_build": 1, "kmap_pairs": 3, "kmap_transpose": 2,
     "count": 2, "voxelize_fwd": 2, "voxelize_bwd": 1, "devoxelize_fwd": 1, "devoxelize_bwd": 2, "ti_weights": 1,
     "v2p_build": 1, "p2v_build": 2, "lift_fwd": 1, "lift_bwd": 1, "conv_gather_f32": 1, "conv_wgrad_f32": 1,
-    "conv_pack_weights": 1, "conv_gather_tc": 1, "conv_wgrad_tc": 1, "to_bf16": 1, "conv_pairs_tc": 1,
+    "conv_pack_weights": 1, "to_bf16": 1, "conv_pairs_tc": 1,
     "conv_reduce": 1, "conv_wgrad_pairs_tc": 1, "kmap_pair_positions": 3, "conv_reduce_bn": 2, "bn_stats": 2,
     "bn_apply": 1, "col_sum": 2, "seg_loss": 3, "confusion_update": 1, "bn_bwd_reduce": 2, "conv_pack_weights_multi": 1, "bn_bwd_apply": 1,
     "conv_os": 3, "conv_os_plan": 13, "conv_wgrad_pairs_tc_det": 2,

@@ -117,24 +117,7 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
   const int ring_bytes = nstages * stage_bytes > staging_bytes ? nstages * stage_bytes : staging_bytes;
   PairsSmemHeader* hdr = (PairsSmemHeader*)(smem + (size_t)((ring_bytes + 127) & ~127));   // ring: nstages <= nkb
 
-  int k = 0, begin, end;
-  if (pairs != nullptr) {
-    if ((int)threadIdx.x <= K) hdr->off[threadIdx.x] = __ldg(off + threadIdx.x);
-    __syncthreads();
-    if (!pair_tile(hdr->off, K, blockIdx.x, kTileRows, &k, &begin, &end)) {          // uniform per CTA
-      pdl_wait();
-      return;
-    }
-  } else {
-    begin = blockIdx.x * kTileRows;
-    end = (int)min((int64_t)begin + kTileRows, n_identity);
-    if (begin >= end) {
-      pdl_wait();
-      return;
-    }
-  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&hdr->full[s], kPProducers + 1);
@@ -144,7 +127,22 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)tmem_cols);
-  if (tid < kPProducers) {
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();       // launch, barrier and TMEM set-up ran under the predecessor's tail; every global read is below
+  int k = 0, begin = 0, end = 0;
+  bool live;
+  if (pairs != nullptr) {
+    if (tid <= K) hdr->off[tid] = __ldg(off + tid);
+    __syncthreads();
+    live = pair_tile(hdr->off, K, blockIdx.x, kTileRows, &k, &begin, &end);          // uniform per CTA
+  } else {
+    begin = blockIdx.x * kTileRows;
+    end = (int)min((int64_t)begin + kTileRows, n_identity);
+    live = begin < end;
+  }
+  if (live && tid < kPProducers) {
     const int p = begin + tid;
     int g = -1;
     if (p < end) {
@@ -157,12 +155,13 @@ conv_pairs_tc_kernel(const __nv_bfloat16* __restrict__ in, const int2* __restric
     }
     hdr->idx[tid] = g;
   }
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  pdl_enter();      // launch, barrier/TMEM set-up and the pair-index loads (static geometry) ran under the predecessor
+  pdl_trigger();
   const uint32_t tmem_base = hdr->tmem_base;
 
+  if (!live) {
+    // no tile for this CTA (the grid is sized from an upper bound of the pair count)
+  } else
   if (warp < 4) {
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % nstages;
@@ -276,26 +275,6 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
   V3Header* hdr = reinterpret_cast<V3Header*>(reinterpret_cast<uint8_t*>(staging) + 4 * kV3StageFloats * sizeof(float));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- schedule: this CTA's run of tiles
-  int T;
-  if (pairs != nullptr) {
-    if (tid <= K) hdr->off[tid] = __ldg(off + tid);
-    __syncthreads();
-    T = 0;
-    for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
-  } else {
-    T = (int)((n_identity + kTileRows - 1) / kTileRows);
-    if (tid == 0) hdr->off[0] = 0, hdr->off[1] = (int32_t)n_identity;     // identity gather = one offset of n rows
-    K = 1;
-  }
-  const int chunk = (T + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int g0 = (int)blockIdx.x * chunk;
-  const int g1 = g0 + chunk < T ? g0 + chunk : T;
-  if (g0 >= g1) {                                          // uniform per CTA
-    pdl_wait();
-    return;
-  }
-
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
       mbar_init(&hdr->full_a[s], kPProducers);
@@ -313,9 +292,28 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_enter();      // launch, schedule, barrier and TMEM set-up ran under the predecessor's tail
+  pdl_wait();       // launch, barrier and TMEM set-up ran under the predecessor's tail; every global read is below
+  // ---- schedule: this CTA's run of tiles
+  int T;
+  if (pairs != nullptr) {
+    if (tid <= K) hdr->off[tid] = __ldg(off + tid);
+    __syncthreads();
+    T = 0;
+    for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
+  } else {
+    T = (int)((n_identity + kTileRows - 1) / kTileRows);
+    if (tid == 0) hdr->off[0] = 0, hdr->off[1] = (int32_t)n_identity;     // identity gather = one offset of n rows
+    K = 1;
+    __syncthreads();
+  }
+  pdl_trigger();
+  const int chunk = (T + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int g0 = (int)blockIdx.x * chunk;
+  const int g1 = g0 + chunk < T ? g0 + chunk : T;          // g0 >= g1: no tiles for this CTA (uniform)
   const uint32_t tmem_base = hdr->tmem_base;
 
+  if (g0 >= g1) {
+  } else
   if (warp < 4) {
     // ------------------------------------------------------------------ gather producers
     uint32_t cnt = 0;
@@ -581,131 +579,6 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bf
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad (bf16 inputs)
-constexpr int kWgPairsPerCta = 512;   // pairs reduced by one CTA = 4 stages of 128, all in flight
-constexpr int kWgStages = kWgPairsPerCta / kTileRows;
-
-struct WgSmemHeader {
-  uint64_t full[kWgStages];
-  uint64_t accum_full;
-  uint32_t tmem_base;
-  int32_t off[40];
-  int32_t pa[kWgStages][kTileRows];
-  int32_t pb[kWgStages][kTileRows];
-};
-
-__global__ void __launch_bounds__(kPThreads)
-conv_wgrad_pairs_tc_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                           const int2* __restrict__ pairs, const int32_t* __restrict__ off, int K, int ca,
-                           int64_t n_identity, int cin, int cout, float* __restrict__ gw, int nstages_fit,
-                           int tmem_cols) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int nb_blocks = (cout + 63) / 64;
-  const int stage_bytes = (2 + nb_blocks) * kBlockBytes;
-  WgSmemHeader* hdr = (WgSmemHeader*)(smem + (size_t)nstages_fit * stage_bytes);
-  const int rows_per_cta = nstages_fit * kTileRows;
-
-  int k = 0, begin, end;
-  if (pairs != nullptr) {
-    if ((int)threadIdx.x <= K) hdr->off[threadIdx.x] = __ldg(off + threadIdx.x);
-    __syncthreads();
-    if (!pair_tile(hdr->off, K, blockIdx.x, rows_per_cta, &k, &begin, &end)) {
-      pdl_wait();
-      return;
-    }
-  } else {
-    begin = blockIdx.x * rows_per_cta;
-    end = (int)min((int64_t)begin + rows_per_cta, n_identity);
-    if (begin >= end) {
-      pdl_wait();
-      return;
-    }
-  }
-  const int mb = blockIdx.y;
-  const int m_valid = cin - mb * 128 < 128 ? cin - mb * 128 : 128;
-  const int niter = (end - begin + kTileRows - 1) / kTileRows;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-    for (int s = 0; s < niter; ++s) mbar_init(&hdr->full[s], kPProducers);
-    mbar_init(&hdr->accum_full, 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)tmem_cols);
-  if (tid < kPProducers) {
-    for (int s = 0; s < niter; ++s) {
-      const int p = begin + s * kTileRows + tid;
-      int ia = -1, ib = -1;
-      if (p < end) {
-        if (pairs != nullptr) {
-          int2 pr = __ldg(pairs + p);
-          ia = ca ? pr.y : pr.x;
-          ib = ca ? pr.x : pr.y;
-        } else {
-          ia = ib = p;
-        }
-      }
-      hdr->pa[s][tid] = ia;
-      hdr->pb[s][tid] = ib;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_enter();
-  const uint32_t tmem_base = hdr->tmem_base;
-
-  if (warp < 4) {
-    for (int s = 0; s < niter; ++s) {
-      uint8_t* st = smem + (size_t)s * stage_bytes;
-      for (int blk = 0; blk * 64 < m_valid; ++blk) {
-        const int width = m_valid - blk * 64 < 64 ? m_valid - blk * 64 : 64;
-        gather_block_bf16(st + blk * kBlockBytes, a, cin, mb * 128 + blk * 64, width >> 3, tid, hdr->pa[s]);
-      }
-      for (int blk = 0; blk < nb_blocks; ++blk) {
-        const int width = cout - blk * 64 < 64 ? cout - blk * 64 : 64;
-        gather_block_bf16(st + (2 + blk) * kBlockBytes, b, cout, blk * 64, width >> 3, tid, hdr->pb[s]);
-      }
-      cp_async_arrive_noinc(&hdr->full[s]);
-    }
-    mbar_wait(&hdr->accum_full, 0);
-    tc_fence_after();
-    float* grow = gw + ((int64_t)k * cin + mb * 128 + tid) * cout;
-    for (int c0 = 0; c0 < cout; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (tid < m_valid) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          atomicAdd(reinterpret_cast<float4*>(grow + c0 + j),
-                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                __uint_as_float(v[j + 3])));
-      }
-    }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, cout, 1, 1);
-      for (int s = 0; s < niter; ++s) {
-        mbar_wait(&hdr->full[s], 0);
-        fence_proxy_async_smem();
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + 2 * kBlockBytes;
-        for (int kk = 0; kk < kTileRows / 16; ++kk) {
-          const uint64_t da = smem_desc_sw128(a_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
-          const uint64_t db = smem_desc_sw128(b_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (s | kk) != 0);
-        }
-      }
-      umma_commit(&hdr->accum_full);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
-}
-
 // The unit line [0, U) of the persistent wgrad kernel (unit u = Cin block u / T, tile u % T) is cut at the CTA run
 // boundaries (multiples of `chunk`) and at the starts of the non-empty (Cin block, offset) groups; the pieces between
 // cuts are the SEGMENTS, each flushed exactly once.  Index of the segment that starts at unit `pos` = number of
@@ -806,27 +679,6 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
   Wg2Header* hdr = reinterpret_cast<Wg2Header*>(reinterpret_cast<uint8_t*>(staging) + 4 * kV3StageFloats * sizeof(float));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  int T;
-  if (pairs != nullptr) {
-    if (tid <= K) hdr->off[tid] = __ldg(off + tid);
-    __syncthreads();
-    T = 0;
-    for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
-  } else {
-    T = (int)((n_identity + kTileRows - 1) / kTileRows);
-    if (tid == 0) hdr->off[0] = 0, hdr->off[1] = (int32_t)n_identity;
-    K = 1;
-  }
-  const int MB = (cin + 127) / 128;
-  const int U = T * MB;
-  const int chunk = (U + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int u0 = (int)blockIdx.x * chunk;
-  const int u1 = u0 + chunk < U ? u0 + chunk : U;
-  if (u0 >= u1) {                                          // uniform per CTA
-    pdl_wait();
-    return;
-  }
-
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
       mbar_init(&hdr->full[s], kPProducers);
@@ -842,7 +694,25 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_enter();
+  pdl_wait();       // set-up ran under the predecessor's tail; every global read is below
+  int T;
+  if (pairs != nullptr) {
+    if (tid <= K) hdr->off[tid] = __ldg(off + tid);
+    __syncthreads();
+    T = 0;
+    for (int k = 0; k < K; ++k) T += (hdr->off[k + 1] - hdr->off[k] + kTileRows - 1) / kTileRows;
+  } else {
+    T = (int)((n_identity + kTileRows - 1) / kTileRows);
+    if (tid == 0) hdr->off[0] = 0, hdr->off[1] = (int32_t)n_identity;
+    K = 1;
+    __syncthreads();
+  }
+  pdl_trigger();
+  const int MB = (cin + 127) / 128;
+  const int U = T * MB;
+  const int chunk = (U + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int u0 = (int)blockIdx.x * chunk;
+  const int u1 = u0 + chunk < U ? u0 + chunk : U;          // u0 >= u1: nothing for this CTA (uniform)
   const uint32_t tmem_base = hdr->tmem_base;
 
   // unit u = (Cin block u / T, tile u % T); walked with an O(1) cursor
@@ -866,6 +736,8 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
     }
   };
 
+  if (u0 >= u1) {
+  } else
   if (warp < 4) {
     // ------------------------------------------------------------------ gather producers
     UnitCursor uc;
@@ -1237,60 +1109,17 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
                "ft3d_conv_wgrad_pairs_tc: unsupported shape cin=%d cout=%d", cin, cout);
   FT3D_REQUIRE(((uintptr_t)a_bf16 & 15) == 0 && ((uintptr_t)b_bf16 & 15) == 0 && ((uintptr_t)gw & 15) == 0,
                "ft3d_conv_wgrad_pairs_tc: pointers must be 16-byte aligned");
-  const int nb_blocks = (cout + 63) / 64;
-  {
-    static int use_v2 = -1;
-    if (use_v2 < 0) {
-      const char* e = getenv("FT3D_WGRAD_PERSISTENT");
-      use_v2 = (e == nullptr || e[0] != '0') ? 1 : 0;
-    }
-    if (use_v2) {
-      const int a_blocks = cin <= 64 ? 1 : 2;
-      const int stage = (a_blocks + nb_blocks) * tc::kBlockBytes;
-      const int fixed = 4 * kV3StageFloats * (int)sizeof(float) + (int)sizeof(Wg2Header) + 1024;
-      const int tcols = tmem_cols_pow2(cout);
-      // two resident CTAs (3-deep rings) when shared memory and TMEM (2 accumulators each) allow, else one CTA
-      int ctas_per_sm = 1, nslots = (226 * 1024 - fixed) / stage;
-      if (fixed + 3 * stage <= 113 * 1024 && 4 * tcols <= 512) {
-        ctas_per_sm = 2;
-        nslots = (113 * 1024 - fixed) / stage;
-      }
-      if (nslots > kWg2MaxSlots) nslots = kWg2MaxSlots;
-      FT3D_REQUIRE(nslots >= 2, "ft3d_conv_wgrad_pairs_tc: tile does not fit shared memory");
-      const int smem_bytes = fixed + nslots * stage;
-      static int configured2 = 0;
-      if (!configured2) {
-        FT3D_CUDA(cudaFuncSetAttribute(conv_wgrad_pairs_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       227 * 1024));
-        configured2 = 1;
-      }
-      const int64_t tiles = (max_pairs + tc::kTileRows - 1) / tc::kTileRows + (pairs ? K : 0);
-      const int64_t units = tiles * ((cin + 127) / 128);
-      const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
-      const unsigned grid = (unsigned)(units < cap ? units : cap);
-      launch_pdl(conv_wgrad_pairs_tc_v2_kernel, dim3(grid), dim3(kV3Threads), smem_bytes, (cudaStream_t)stream, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs,
-          cin, cout, gw, nslots, tcols, a_blocks, (float*)nullptr);
-      return check_launch("ft3d_conv_wgrad_pairs_tc");
-    }
+  Wg2Launch l;
+  FT3D_REQUIRE(wg2_launch(cin, cout, K, max_pairs, pairs != nullptr, &l) == 0,
+               "ft3d_conv_wgrad_pairs_tc: tile does not fit shared memory");
+  static int configured2 = 0;
+  if (!configured2) {
+    FT3D_CUDA(cudaFuncSetAttribute(conv_wgrad_pairs_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured2 = 1;
   }
-  const int stage_bytes = (2 + nb_blocks) * tc::kBlockBytes;
-  const int tail = (int)sizeof(WgSmemHeader) + 1024;
-  // two resident CTAs when two stages of each fit in half the shared memory, else one CTA with up to 4 stages
-  int nst = (112 * 1024 - tail) / stage_bytes;
-  if (nst < 2) nst = (226 * 1024 - tail) / stage_bytes;
-  if (nst > kWgStages) nst = kWgStages;
-  FT3D_REQUIRE(nst >= 1, "ft3d_conv_wgrad_pairs_tc: tile does not fit shared memory");
-  const int smem_bytes = nst * stage_bytes + tail;
-  static int configured = 0;
-  if (!configured) {
-    FT3D_CUDA(cudaFuncSetAttribute(conv_wgrad_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 1;
-  }
-  const int rows = nst * tc::kTileRows;
-  const int64_t items = (max_pairs + rows - 1) / rows + (pairs ? K : 0);
-  dim3 grid((unsigned)items, (unsigned)((cin + 127) / 128));
-  launch_pdl(conv_wgrad_pairs_tc_kernel, dim3(grid), dim3(kPThreads), smem_bytes, (cudaStream_t)stream, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca, max_pairs, cin,
-      cout, gw, nst, tmem_cols_pow2(cout));
+  launch_pdl(conv_wgrad_pairs_tc_v2_kernel, dim3(l.grid), dim3(kV3Threads), l.smem_bytes, (cudaStream_t)stream,
+             (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, (const int2*)pairs, pair_offsets, K, ca,
+             max_pairs, cin, cout, gw, l.nslots, l.tcols, l.a_blocks, (float*)nullptr);
   return check_launch("ft3d_conv_wgrad_pairs_tc");
 }
 

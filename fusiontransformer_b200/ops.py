@@ -396,31 +396,6 @@ def packed_weights(w: torch.Tensor, w_transposed: bool, owner=None) -> torch.Ten
     return img
 
 
-def conv_gather_tc(inp, nbr, k, kflip, w, w_transposed, owner=None):
-    """Same contract as conv_gather_f32 on the tcgen05 tensor cores (bf16 operands, fp32 accumulate)."""
-    inp = _chk(inp, torch.float32, "inp")
-    nbr = _chk(nbr, torch.int32, "nbr")
-    n_out, kpad = nbr.shape
-    cin, cout = w.shape[-2], w.shape[-1]
-    red, ncols = (cout, cin) if w_transposed else (cin, cout)
-    if inp.shape[1] != red:
-        raise Ft3dError("conv: feature width %d != %d" % (inp.shape[1], red))
-    img = packed_weights(w, w_transposed, owner)
-    out = torch.empty((n_out, ncols), dtype=torch.float32, device=inp.device)
-    lib().conv_gather_tc(inp.data_ptr(), nbr.data_ptr(), n_out, k, kpad, int(kflip), red, ncols, img.data_ptr(),
-                         out.data_ptr(), _stream())
-    return out
-
-
-def conv_wgrad_tc(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
-    a = _chk(a, torch.float32, "a")
-    b = _chk(b, torch.float32, "b")
-    gw = torch.zeros((k, cin, cout), dtype=torch.float32, device=a.device)
-    lib().conv_wgrad_tc(a.data_ptr(), b.data_ptr(), pairs.data_ptr(), pair_offsets.data_ptr(), k, int(ca), cin,
-                        cout, int(max_pairs), gw.data_ptr(), _stream())
-    return gw
-
-
 # ----------------------------------------------------------------------------- pair-major tensor-core path
 def to_bf16(x: torch.Tensor) -> torch.Tensor:
     x = _chk(x, torch.float32, "x")

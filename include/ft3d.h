@@ -151,9 +151,9 @@ int ft3d_lift_bwd(const float* gout, int64_t sb, int64_t sc, int64_t sh, int64_t
 int ft3d_conv_gather_f32(const float* in, const int32_t* nbr, int64_t n_out, int32_t K,
                          int32_t kpad, int32_t kflip, int32_t red, int32_t ncols, const float* w,
                          int32_t w_transposed, float* out, ft3d_stream_t stream);
-/* bf16 tcgen05 variant: operands rounded to bf16, fp32 accumulation in TMEM.  `wpacked` is the
- * image written by ft3d_conv_pack_weights for the same (K, cin, cout, w_transposed): per offset and
- * 64-wide reduction block one [ncols x 128 B] swizzled bf16 tile, streamed with cp.async.bulk.
+/* Weight images of the bf16 tcgen05 kernels (ft3d_conv_os, ft3d_conv_pairs_tc): operands rounded to bf16, fp32
+ * accumulation in TMEM.  `wpacked` is the image written by ft3d_conv_pack_weights for (K, cin, cout, w_transposed):
+ * per offset and 64-wide reduction block one [ncols x 128 B] swizzled bf16 tile, streamed with cp.async.bulk.
  * Supported: red % 16 == 0 (16..512), ncols % 32 == 0 (32..256, or 384). */
 size_t ft3d_conv_packed_bytes(int32_t K, int32_t red, int32_t ncols);
 int ft3d_conv_pack_weights(const float* w, int32_t K, int32_t cin, int32_t cout,
@@ -163,9 +163,6 @@ int ft3d_conv_pack_weights(const float* w, int32_t K, int32_t cin, int32_t cout,
  * ft3d_conv_pack_desc_bytes()), chunk_begin = running sum of ft3d_conv_packed_bytes(...)/16 of the records before. */
 size_t ft3d_conv_pack_desc_bytes(void);
 int ft3d_conv_pack_weights_multi(const void* desc, int32_t n_desc, int64_t total_chunks, ft3d_stream_t stream);
-int ft3d_conv_gather_tc(const float* in, const int32_t* nbr, int64_t n_out, int32_t K,
-                        int32_t kpad, int32_t kflip, int32_t red, int32_t ncols,
-                        const void* wpacked, float* out, ft3d_stream_t stream);
 /* wgrad: gw[k] += sum over pairs p of offset k of  a[pairs[p,ca],:]^T  b[pairs[p,cb],:]
  *   forward conv : a = features [.,cin], ca = 0 ; b = grad_out [.,cout], cb = 1
  *   transposed   : ca = 1, cb = 0 (pair columns swapped, models/spvcnn.py:42-46)
@@ -174,9 +171,6 @@ int ft3d_conv_gather_tc(const float* in, const int32_t* nbr, int64_t n_out, int3
 int ft3d_conv_wgrad_f32(const float* a, const float* b, const int32_t* pairs,
                         const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
                         int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
-int ft3d_conv_wgrad_tc(const float* a, const float* b, const int32_t* pairs,
-                       const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
-                       int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
 
 /* Pair-major tensor-core path (the default): gather -> GEMM -> sorted, atomic-free scatter.
  *   ft3d_to_bf16        : activations / gradients rounded once to bf16 (dst holds n bf16).

@@ -10,8 +10,8 @@ from fusiontransformer_b200 import _lib
 def test_header_parses():
     protos = _lib.parse_header()
     assert len(protos) >= 30
-    for must in ("ft3d_hash", "ft3d_quantize", "ft3d_kmap_build", "ft3d_kmap_pairs", "ft3d_conv_gather_tc",
-                 "ft3d_conv_wgrad_tc", "ft3d_conv_gather_f32", "ft3d_devoxelize_fwd", "ft3d_lift_fwd",
+    for must in ("ft3d_hash", "ft3d_quantize", "ft3d_kmap_build", "ft3d_kmap_pairs", "ft3d_conv_os",
+                 "ft3d_conv_os_plan", "ft3d_conv_gather_f32", "ft3d_devoxelize_fwd", "ft3d_lift_fwd",
                  "ft3d_last_error", "ft3d_version"):
         assert must in protos, must
     res, args = protos["ft3d_hash"]
@@ -35,10 +35,13 @@ def test_host_only_entry_points():
     assert L.conv_packed_bytes(27, 96, 128) == 27 * 2 * 128 * 128
     assert L.unique_workspace(1000) > 1000 * 8
     # argument validation happens before any CUDA call, so it is testable without a GPU
-    with pytest.raises(_lib.Ft3dError, match="bad K"):
-        L.conv_gather_tc(16, 16, 10, 40, 32, 0, 64, 64, 16, 16, None)
-    with pytest.raises(_lib.Ft3dError, match="unsupported shape"):
-        L.conv_gather_tc(16, 16, 10, 27, 32, 0, 20, 64, 16, 16, None)
+    with pytest.raises(_lib.Ft3dError, match="bad arguments"):          # K > 32
+        L.conv_os(256, 10, 256, 256, 256, 256, 256, 256, 8, 1, 0, 40, 0, 64, 64, 256, 256, 128, None, 0.0, 0.0, None,
+                  None, None, None, 0, None, None)
+    with pytest.raises(_lib.Ft3dError, match="unsupported shape"):      # red % 16 != 0
+        L.conv_os(256, 10, 256, 256, 256, 256, 256, 256, 8, 1, 0, 27, 0, 20, 64, 256, 256, 128, None, 0.0, 0.0, None,
+                  None, None, None, 0, None, None)
+    assert L.conv_os_plan_workspace(1000, 32) > 5 * 1000 * 4 and L.conv_os_workspace(128, 4) >= 4 * 128 * 128 * 4
 
 
 def test_no_cpu_fallback():

@@ -160,3 +160,27 @@ def test_device_seg_iou_matches_reference_metric_fixture():
     np.testing.assert_allclose(m.iou.cpu().numpy(), g["iou"], rtol=1e-6, equal_nan=True)
     pred = torch.from_numpy(g["logits1"]).cuda().argmax(1)
     np.testing.assert_array_equal(pred[torch.from_numpy(g["inverse_map"]).cuda()].cpu().numpy(), g["pred_points"])
+
+
+@pytest.mark.gpu
+def test_device_batch_path_matches_reference_collate_fixture():
+    """a3 on the GPU: dataflow.voxelize_batch (scale + bounds + dedup + select + batch column for the whole batch in
+    two libft3d calls) against the tensors FusionTransformer/data/collate.py:6-86 `collate_scn_base` produced from the
+    per-scan CPU pipeline (tests/golden/ref_collate.npz, generated by running the reference's collate): coordinates,
+    features and voxel labels of the batch, row for row."""
+    from fusiontransformer_b200 import dataflow
+    from fusiontransformer_b200.synthetic import make_scan
+    g = np.load(os.path.join(GOLD, "ref_collate.npz"))
+    scans = [make_scan("nuscenes", 20 + i) for i in range(3)]
+    db = dataflow.to_device(dataflow.host_batch_from_scans(scans), "cuda")
+    lidar, rc, bidx, labels, inv, kept = dataflow.voxelize_batch(db)
+    np.testing.assert_array_equal(lidar.C.cpu().numpy(), g["C"])
+    np.testing.assert_array_equal(lidar.F.cpu().numpy(), g["F"])
+    np.testing.assert_array_equal(labels.cpu().numpy(), g["seg_label"])
+    np.testing.assert_array_equal(bidx.cpu().numpy(), g["C"][:, 3])
+    off = 0
+    for i in range(3):                       # per-scan pieces of the fixture, in batch order
+        n = len(g["coords%d" % i])
+        np.testing.assert_array_equal(lidar.C[off:off + n, :3].cpu().numpy(), g["coords%d" % i])
+        off += n
+    assert off == lidar.C.shape[0]
