@@ -146,6 +146,13 @@ class ReLU(nn.ReLU):
         return t
 
 
+class Linear(nn.Linear):
+    """nn.Linear whose GEMM follows ts.OPERAND_DTYPE (same parameters / state_dict as nn.Linear)."""
+
+    def forward(self, x):
+        return ts.linear(x, self.weight, self.bias)
+
+
 def _conv_bn_relu(inc, outc, ks, stride, transpose=False):
     return nn.Sequential(Conv3d(inc, outc, ks, stride=stride, transpose=transpose), BatchNorm(outc), ReLU(True))
 
@@ -197,9 +204,9 @@ class SPVCNN(nn.Module):
                 _Block(cs[4 + i], cs[5 + i], 2, 2, transpose=True),
                 nn.Sequential(ResidualBlock(cs[5 + i] + skips[i], cs[5 + i]), ResidualBlock(cs[5 + i], cs[5 + i]))]))
         self.point_transforms = nn.ModuleList([
-            nn.Sequential(nn.Linear(cs[0], cs[4]), nn.BatchNorm1d(cs[4]), nn.ReLU(True)),
-            nn.Sequential(nn.Linear(cs[4], cs[6]), nn.BatchNorm1d(cs[6]), nn.ReLU(True)),
-            nn.Sequential(nn.Linear(cs[6], cs[8]), nn.BatchNorm1d(cs[8]), nn.ReLU(True))])
+            nn.Sequential(Linear(cs[0], cs[4]), nn.BatchNorm1d(cs[4]), nn.ReLU(True)),
+            nn.Sequential(Linear(cs[4], cs[6]), nn.BatchNorm1d(cs[6]), nn.ReLU(True)),
+            nn.Sequential(Linear(cs[6], cs[8]), nn.BatchNorm1d(cs[8]), nn.ReLU(True))])
         for m in self.modules():
             if isinstance(m, nn.BatchNorm1d):
                 nn.init.constant_(m.weight, 1)
@@ -261,9 +268,9 @@ class Net3DSeg(SPVCNN):
         super().__init__(**(backbone_3d_kwargs or {}))
         self.fusion = fusion
         if fusion == "middle":
-            self.middle_fusion_transform = nn.Sequential(nn.Linear(96, self.cs[4]), nn.BatchNorm1d(self.cs[4]), nn.ReLU(True))
+            self.middle_fusion_transform = nn.Sequential(Linear(96, self.cs[4]), nn.BatchNorm1d(self.cs[4]), nn.ReLU(True))
         elif fusion == "early":
-            self.early_fusion_transform = nn.Sequential(nn.Linear(96, 32), nn.BatchNorm1d(32), nn.ReLU(True))
+            self.early_fusion_transform = nn.Sequential(Linear(96, 32), nn.BatchNorm1d(32), nn.ReLU(True))
         self.linear = nn.Linear(self.cs[-1], num_classes)
         self.dual_head = dual_head
         if dual_head:

@@ -253,6 +253,17 @@ class _RoundedConv(torch.autograd.Function):
         return None, gf, gk
 
 
+def linear(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
+    """nn.Linear of the point-branch / fusion MLPs (models/spvcnn.py:164-180, middle_fusion.py:18-22).  With
+    OPERAND_DTYPE == "bf16" the layers the product runs on tensor cores (in/out multiples of 32, out <= 256: a14 on
+    the tcgen05 identity-gather GEMM) round their GEMM operands like the convolutions do; the bias add stays fp32."""
+    out_f, in_f = weight.shape
+    if OPERAND_DTYPE is not None and in_f % 32 == 0 and out_f % 32 == 0 and in_f <= 384 and out_f <= 256:
+        y = _RoundedConv.apply(lambda f, k: f.matmul(k.t()), x, weight)
+        return y if bias is None else y + bias
+    return torch.nn.functional.linear(x, weight, bias)
+
+
 def sparseconv(feats: torch.Tensor, kernel: torch.Tensor, pairs: torch.Tensor, counts: torch.Tensor,
                sizes, transpose: bool) -> torch.Tensor:
     """Offset-by-offset gather -> mm -> scatter-add (App. A.6 arithmetic), autograd via torch."""

@@ -1,0 +1,128 @@
+"""Gradient fidelity of the bf16 tensor-core mode, measured instead of argued (VERDICT r1 "weak" 2).
+
+1. Conditioning: the fp64 CPU oracle is the ground truth.  Against it we measure, tensor by tensor, the parameter
+   gradients of (a) the fp32 oracle, (b) the oracle evaluating the product's arithmetic specification (conv / linear
+   operands rounded to bf16, fp32 accumulation) and (c) the GPU in tc mode.  The 50-BatchNorm network amplifies any
+   2^-9 perturbation of the forward activations at random initialisation, so (b) itself is far from fp64; the claim
+   under test is that the GPU is no further from the truth than its own specification is.
+2. Convergence: 200 optimiser steps on a fixed batch from the same seed in exact fp32 mode and in tc mode -- the two
+   loss curves must stay together, i.e. the bf16 gradients train like the fp32 ones.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _param_grads(net):
+    return {n: p.grad.detach().double().cpu() for n, p in net.named_parameters() if p.grad is not None}
+
+
+def _errors(got, truth):
+    gmax = max(v.norm().item() for v in truth.values())
+    out = []
+    for n, t in truth.items():
+        if t.norm().item() < 1e-4 * gmax:        # analytically-zero gradients (Linear bias under BatchNorm): noise
+            continue
+        out.append(((got[n] - t).norm() / t.norm()).item())
+    return np.array(out)
+
+
+def test_tc_gradients_are_as_close_to_fp64_truth_as_their_arithmetic_spec(monkeypatch, small_batch):
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200.spvcnn import Net3DSeg
+    from oracle import ft_glue as og, ts_ops as ts
+    coords, feats = small_batch["coords"], small_batch["feats"]
+    n = coords.shape[0]
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(n, 96, generator=g)
+    labels = torch.randint(0, 20, (n,), generator=g)
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def oracle_run(dtype, operand):
+        monkeypatch.setattr(ts, "OPERAND_DTYPE", operand)
+        torch.manual_seed(1)
+        net = og.Net3DSeg(num_classes=20, dual_head=False, fusion="middle").to(dtype).train()
+        net.dropout.p = 0.0
+        out = net(ts.SparseTensor(feats.to(dtype), coords), img.to(dtype))
+        loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], labels)
+        loss.backward()
+        return loss.item(), _param_grads(net), net
+
+    l64, g64, _ = oracle_run(torch.float64, None)
+    l32, g32, o32 = oracle_run(torch.float32, None)
+    lbf, gbf, _ = oracle_run(torch.float32, "bf16")
+    monkeypatch.setenv("FT3D_CONV", "tc")
+    net = Net3DSeg(num_classes=20, dual_head=False, fusion="middle")
+    net.load_state_dict(o32.state_dict())
+    net = net.cuda().train()
+    net.dropout.p = 0.0
+    out = net(ft.SparseTensor(feats.cuda(), coords.cuda()), img.cuda())
+    loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], labels.cuda())
+    loss.backward()
+    ggpu = _param_grads(net)
+    e32, ebf, egpu = _errors(g32, g64), _errors(gbf, g64), _errors(ggpu, g64)
+    print("\nloss: fp64 %.6f  fp32 %.6f  bf16-spec %.6f  gpu-tc %.6f" % (l64, l32, lbf, loss.item()))
+    for name, e in (("oracle fp32", e32), ("oracle bf16-spec", ebf), ("GPU tc", egpu)):
+        print("  %-18s gradient rel-L2 vs fp64 truth: median %.3e  p90 %.3e  worst %.3e" %
+              (name, np.median(e), np.percentile(e, 90), e.max()))
+    # the loss itself is well conditioned: all three agree with the truth
+    assert abs(l32 - l64) < 1e-5 * l64 and abs(lbf - l64) < 2e-3 * l64 and abs(loss.item() - l64) < 2e-3 * l64
+    # fp32 arithmetic reproduces the truth; bf16 operand rounding ALONE (CPU, no GPU involved) already moves the
+    # gradients by orders of magnitude more -- the network's conditioning, not a kernel property
+    assert np.median(e32) < 1e-3
+    assert np.median(ebf) > 20 * np.median(e32)
+    # the GPU is no further from the truth than the specification it implements
+    assert np.median(egpu) < 1.5 * np.median(ebf) + 1e-3
+    assert np.percentile(egpu, 90) < 1.5 * np.percentile(ebf, 90) + 1e-3
+
+
+def _train_curve(mode, steps, monkeypatch):
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import dataflow
+    from fusiontransformer_b200.dp import GradSync
+    from fusiontransformer_b200.spvcnn import Net3DSeg
+    from fusiontransformer_b200.synthetic import make_scan
+    monkeypatch.setenv("FT3D_CONV", mode)
+    torch.manual_seed(1)
+    net = Net3DSeg(num_classes=20, dual_head=False, fusion="middle").cuda().train()
+    net.dropout.p = 0.0
+    sync = GradSync(net)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    hb = dataflow.host_batch_from_scans([make_scan("nuscenes", i) for i in range(2)])
+    plan = dataflow.prepare_batch(hb, "cuda")
+    ex = plan.extras
+    g = torch.Generator(device="cuda").manual_seed(5)
+    img = torch.randn(ex["lidar"].C.shape[0], 96, device="cuda", generator=g)
+    # learnable labels: a function of the voxel position, so that the loss can actually go down
+    labels = ((ex["lidar"].C[:, 0] // 64 + ex["lidar"].C[:, 1] // 64) % 20).long()
+    losses = []
+    for _ in range(steps):
+        plan = dataflow.prepare_batch(hb, "cuda")
+        out = net(plan.extras["lidar"], img, plan=plan)
+        loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], labels)
+        sync.zero_grad()
+        loss.backward()
+        sync.finish()
+        opt.step()
+        losses.append(loss.item())
+    return np.array(losses)
+
+
+def test_tc_mode_trains_like_fp32_mode(monkeypatch):
+    steps = 200
+    lf = _train_curve("f32", steps, monkeypatch)
+    lt = _train_curve("tc", steps, monkeypatch)
+    # windowed means (the per-step loss of two chaotic trajectories differs; the curves must not)
+    w = 20
+    mf = lf.reshape(-1, w).mean(1)
+    mt = lt.reshape(-1, w).mean(1)
+    rel = np.abs(mt - mf) / mf
+    print("\nloss, mean of each %d-step window\n  f32: %s\n  tc : %s\n  rel: %s" %
+          (w, np.round(mf, 4), np.round(mt, 4), np.round(rel, 4)))
+    assert lf[-w:].mean() < 0.5 * lf[:5].mean() and lt[-w:].mean() < 0.5 * lt[:5].mean()     # both train
+    assert rel[0] < 0.02                     # identical start: first window within 2 %
+    assert rel.max() < 0.10 and np.median(rel) < 0.05
