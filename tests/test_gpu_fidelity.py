@@ -124,5 +124,6 @@ def test_tc_mode_trains_like_fp32_mode(monkeypatch):
     print("\nloss, mean of each %d-step window\n  f32: %s\n  tc : %s\n  rel: %s" %
           (w, np.round(mf, 4), np.round(mt, 4), np.round(rel, 4)))
     assert lf[-w:].mean() < 0.5 * lf[:5].mean() and lt[-w:].mean() < 0.5 * lt[:5].mean()     # both train
-    assert rel[0] < 0.02                     # identical start: first window within 2 %
-    assert rel.max() < 0.10 and np.median(rel) < 0.05
+    # every window within 2 % of the fp32 curve, or within 2e-3 absolute once the fixed batch is overfitted and the
+    # loss itself is ~1e-3 (measured on B200: 0.2 % while the loss is O(1), 2.2 % at 0.07, then |diff| <= 5e-4)
+    assert np.all(np.abs(mt - mf) < 0.02 * mf + 2e-3), rel
