@@ -97,12 +97,35 @@ def os_enabled() -> bool:
     return algo is None or algo == "os"
 
 
+OS_CLUSTER_BY_STRIDE = {1: 1, 2: 1, 4: 1, 8: 1, 16: 1}     # k3 maps: CTAs per cluster sharing the weight blocks
+
+
+def os_cluster_for_stride(stride: int) -> int:
+    m = _environ.get("FT3D_OS_CLUSTER_MAP")          # e.g. "4:2,8:2,16:4"
+    if m:
+        for item in m.split(","):
+            s, c = item.split(":")
+            if int(s) == stride:
+                return int(c)
+    return OS_CLUSTER_BY_STRIDE.get(stride, 1)
+
+
+def os_tile_rows(kmap, red: int, ncols: int) -> int:
+    """Rows of a schedule tile = 128 x the CTAs of the thread-block cluster that shares the tile's weight blocks.
+    ``FT3D_OS_CLUSTER`` = 1 | 2 | 4 forces the cluster size; by default it follows the kernel map's tensor stride so
+    that every layer on a map uses ONE schedule (the deep, wide layers are the ones bound by re-streaming B_k)."""
+    cs = _environ.get("FT3D_OS_CLUSTER")
+    if cs is not None and cs != "auto":
+        return 128 * int(cs)
+    return 128 * getattr(kmap, "os_cluster", 1)
+
+
 def os_conv(x16, kmap, kernel, role: str, bn=None):
     """Output-stationary tcgen05 convolution of one layer (csrc/conv_os.cu): -> (y f32 [rows, ncols], stat or None).
     ``bn`` = (eps, momentum, running_mean, running_var): BatchNorm training statistics from the epilogue."""
-    plan, wt, kflip, n_rows = kmap.os_args(role)
     w = kernel.detach()
     cin, cout = w.shape[-2], w.shape[-1]
+    plan, wt, kflip, n_rows = kmap.os_args(role, os_tile_rows(kmap, cin, cout))
     red, ncols = (cout, cin) if wt else (cin, cout)
     if WORK_LOG is not None:
         WORK_LOG.append(dict(kind="conv_os", pairs=kmap.num_pairs(), red=red, ncols=ncols, rows=n_rows, K=kmap.K,

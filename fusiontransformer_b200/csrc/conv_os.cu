@@ -58,6 +58,7 @@ struct OsArgs {
   unsigned long long* trace;  // nullable: per CTA 8 x u64 (globaltimer stamps and counts), tools/conv_os_probe.py
   int64_t n_out;
   int unit_cap, K, kflip, red, ncols, nslots, tcols, nbuf;
+  int cs, tile_rows;          // CTAs per cluster (1, 2, 4) and rows of a schedule tile (128 * cs)
 };
 
 __device__ __forceinline__ void os_cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
@@ -85,6 +86,35 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap
       " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst_smem),
       "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
       : "memory");
+}
+
+// ---- thread-block clusters: the CTAs of a cluster own the 128-row slices of ONE schedule tile of 128*cs rows and walk
+// the same pass list in lockstep, so the weight block B_k of a pass is fetched from L2 once per cluster (rank 0 issues
+// a multicast bulk copy that lands at the same shared-memory offset in every CTA and completes on every CTA's own
+// mbarrier) instead of once per 128 rows.  B is 47-65 % of the kernel's L2 traffic for the 128-256-wide layers.
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// arrives on the mbarrier at the same offset in every CTA of cta_mask once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // walks the passes of this CTA's work units u = first, first + step, ... (units without passes are skipped); the
@@ -135,12 +165,16 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   float* sstat = staging + 4 * kOsStageFloats;                                   // [4 warps][2][ncols]
   OsHeader* hdr = reinterpret_cast<OsHeader*>(sstat + 4 * 2 * ncols);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int step = (int)gridDim.x, first = (int)blockIdx.x;
+  const int cs = a.cs;
+  const int rank = cs > 1 ? (int)cluster_rank() : 0;
+  const int step = (int)gridDim.x / cs, first = (int)blockIdx.x / cs;      // units are dealt to clusters
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const int row_base = rank * kTileRows;                                   // this CTA's slice of a schedule tile
 
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
       mbar_init(&hdr->full[s], TMA ? 1 : kOsProducers + 1);
-      mbar_init(&hdr->empty[s], 1);
+      mbar_init(&hdr->empty[s], (uint32_t)cs);                             // every CTA of the cluster has consumed it
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&hdr->acc_full[b], 1);
@@ -151,6 +185,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)(a.nbuf * a.tcols));
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
   tc_fence_after();
   pdl_enter();      // launch, barrier and TMEM set-up ran under the predecessor's tail; every global read is below
   const uint32_t tmem_base = hdr->tmem_base;
@@ -171,7 +206,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
     const int sub = lane & 7;
     if (it.valid()) {
       k_n = __ldg(a.pass_k + it.pass());
-      r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * kTileRows) + warp * 8 + sub);
+      r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
     }
     uint32_t cnt = 0, npass = 0;
     while (it.valid()) {
@@ -181,7 +216,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
       ++npass;
       if (it.valid()) {                                    // next pass's indices travel under this pass's issue
         k_n = __ldg(a.pass_k + it.pass());
-        r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * kTileRows) + warp * 8 + sub);
+        r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
       }
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         const int slot = (int)(cnt % (uint32_t)nslots);
@@ -190,7 +225,11 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         uint8_t* st = smem + (size_t)slot * stage_bytes;
         if (warp == 0 && lane == 0) {
           mbar_arrive_expect_tx(&hdr->full[slot], (uint32_t)(kBlockBytes + b_bytes));
-          bulk_g2s(st + kBlockBytes, a.wpacked + ((size_t)k * nkb + kb) * b_bytes, (uint32_t)b_bytes, &hdr->full[slot]);
+          const uint8_t* bsrc = a.wpacked + ((size_t)k * nkb + kb) * b_bytes;
+          if (cs == 1)
+            bulk_g2s(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot]);
+          else if (rank == 0)     // one L2 read for the whole cluster; every CTA's full[slot] gets its complete_tx
+            bulk_g2s_multicast(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot], cmask);
         }
         if (lane < 8)
           tma_gather4(smem_u32(st) + (uint32_t)(warp * 8 + lane) * 512u, &tmap, kb * 64, r4.x, r4.y, r4.z, r4.w,
@@ -203,13 +242,13 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
     OsPassIter it;
     it.init(a.units, U, first, step);
     uint32_t cnt = 0, np = 0;
-    int g_n = it.valid() ? __ldg(a.pass_idx + (int64_t)it.pass() * kTileRows + tid) : -1;
+    int g_n = it.valid() ? __ldg(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base + tid) : -1;
     while (it.valid()) {
       const int ib = (int)(np & 1);
       hdr->idx[ib][tid] = g_n;
       it.next();
       ++np;
-      if (it.valid()) g_n = __ldg(a.pass_idx + (int64_t)it.pass() * kTileRows + tid);
+      if (it.valid()) g_n = __ldg(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base + tid);
       os_named_bar_sync(1, kOsProducers);
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         const int slot = (int)(cnt % (uint32_t)nslots);
@@ -282,7 +321,8 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
                           smem_desc_sw128(b_addr + c * ncw * kBlockRowBytes + kk * 32, 16, 1024), idesc,
                           (q | kb | kk) != 0);
             }
-            umma_commit(&hdr->empty[slot]);
+            if (cs == 1) umma_commit(&hdr->empty[slot]);
+            else umma_commit_multicast(&hdr->empty[slot], cmask);
           }
         }
         umma_commit(&hdr->acc_full[buf]);
@@ -315,7 +355,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
       const int4 u0 = u0_n, u1 = u1_n;                     // {first pass, passes, tile, chunks}, {chunk, scratch base}
       if (u + step < U) u0_n = __ldg(a.units + 2 * (int64_t)(u + step)), u1_n = __ldg(a.units + 2 * (int64_t)(u + step) + 1);
       const int tile = u0.z, chunks = u0.w;
-      const int my_row = __ldg(a.out_row + (int64_t)tile * kTileRows + q * 32 + lane);
+      const int my_row = __ldg(a.out_row + (int64_t)tile * a.tile_rows + row_base + q * 32 + lane);
       if (u0.y == 0) {                                     // rows without any neighbour: the result is zero
         if (my_row >= 0)
           for (int c = 0; c < ncols; c += 4)
@@ -327,7 +367,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * a.tcols) + ((uint32_t)(q * 32) << 16);
       // split tile: this unit's partial rows go to its scratch slot, [slot][tile row][ncols]
-      float* part = chunks > 1 ? a.scratch + ((size_t)(u1.y + u1.x) * kTileRows + q * 32) * ncols : nullptr;
+      float* part = chunks > 1 ? a.scratch + ((size_t)(u1.y + u1.x) * a.tile_rows + row_base + q * 32) * ncols : nullptr;
       nsplit_units += chunks > 1 ? 1u : 0u;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
@@ -390,6 +430,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)(a.nbuf * a.tcols));
 }
 
@@ -400,36 +441,36 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
 template <bool STATS>
 __global__ void __launch_bounds__(kColThreads)
 conv_os_fold_kernel(const int4* __restrict__ split_tiles, const int32_t* __restrict__ num,
-                    const int32_t* __restrict__ out_row, const float* __restrict__ scratch, int ncols,
+                    const int32_t* __restrict__ out_row, const float* __restrict__ scratch, int ncols, int tile_rows,
                     float* __restrict__ out, float* __restrict__ partials) {
   pdl_enter();
   __shared__ float4 s_stage[STATS ? kColStageFloat4 : 1];
-  __shared__ int s_rows[kTileRows];
+  __shared__ int s_rows[4 * kTileRows];
   const int ns = __ldg(num + 4);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   if ((int)blockIdx.x < ns) {
     const int4 sp = __ldg(split_tiles + blockIdx.x);       // {tile, units, first scratch slot, -}
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int r = tid; r < kTileRows; r += blockDim.x * blockDim.y) s_rows[r] = __ldg(out_row + (int64_t)sp.x * kTileRows + r);
+    for (int r = tid; r < tile_rows; r += blockDim.x * blockDim.y) s_rows[r] = __ldg(out_row + (int64_t)sp.x * tile_rows + r);
     __syncthreads();
     const int ch = threadIdx.x * 4;
-    const float* p0 = scratch + (size_t)sp.z * kTileRows * ncols + ch;
-    const size_t cstride = (size_t)kTileRows * ncols;
+    const float* p0 = scratch + (size_t)sp.z * tile_rows * ncols + ch;
+    const size_t cstride = (size_t)tile_rows * ncols;
     constexpr int RB = 4;
-    for (int r0 = threadIdx.y; r0 < kTileRows; r0 += RB * blockDim.y) {
+    for (int r0 = threadIdx.y; r0 < tile_rows; r0 += RB * blockDim.y) {
       float4 x[RB][4];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int r = r0 + i * blockDim.y;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          x[i][c] = (r < kTileRows && c < sp.y) ? __ldg(reinterpret_cast<const float4*>(p0 + c * cstride + (size_t)r * ncols))
+          x[i][c] = (r < tile_rows && c < sp.y) ? __ldg(reinterpret_cast<const float4*>(p0 + c * cstride + (size_t)r * ncols))
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int r = r0 + i * blockDim.y;
-        if (r >= kTileRows) break;
+        if (r >= tile_rows) break;
         const int row = s_rows[r];
         if (row < 0) continue;
         float4 acc = x[i][0];
@@ -504,20 +545,22 @@ using namespace ft3d;
 
 extern "C" {
 
-size_t ft3d_conv_os_workspace(int32_t ncols, int64_t scratch_slots) {
+size_t ft3d_conv_os_workspace(int32_t ncols, int64_t scratch_slots, int32_t tile_rows) {
   return os_partials_bytes(ncols, scratch_slots) +
-         align_up((size_t)scratch_slots * tc::kTileRows * (size_t)ncols * sizeof(float), 256);
+         align_up((size_t)scratch_slots * (size_t)tile_rows * (size_t)ncols * sizeof(float), 256);
 }
 
 int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const int32_t* split_tiles,
                  const int32_t* num, const int32_t* out_row, const int32_t* pass_k, const int32_t* pass_idx,
-                 int64_t unit_cap, int64_t tiles, int64_t scratch_slots, int32_t K, int32_t kflip, int32_t red,
+                 int64_t unit_cap, int64_t tiles, int32_t tile_rows, int64_t scratch_slots, int32_t K, int32_t kflip,
+                 int32_t red,
                  int32_t ncols, const void* wpacked, float* out, int64_t n_out, const int32_t* valid_rows, float eps,
                  float momentum, float* stat, float* running_mean, float* running_var, void* workspace,
                  size_t workspace_bytes, void* trace, ft3d_stream_t stream) {
   if (tiles == 0 || n_out == 0) return FT3D_OK;
   FT3D_REQUIRE(in_bf16 && units && num && out_row && pass_k && pass_idx && wpacked && out && K > 0 && K <= 32 &&
-                   n_in > 0 && unit_cap >= tiles && scratch_slots >= 0 && (scratch_slots == 0 || split_tiles),
+                   n_in > 0 && unit_cap >= tiles && scratch_slots >= 0 && (scratch_slots == 0 || split_tiles) &&
+                   (tile_rows == 128 || tile_rows == 256 || tile_rows == 512),
                "ft3d_conv_os: bad arguments");
   FT3D_REQUIRE(red >= 16 && red % 16 == 0 && red <= 512 && ncols >= 32 && ncols % 32 == 0 &&
                    (ncols <= 256 || ncols == 384),
@@ -528,8 +571,8 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
   const bool stats = stat != nullptr;
   FT3D_REQUIRE((!stats && scratch_slots == 0) ||
                    (workspace && ((uintptr_t)workspace & 255) == 0 &&
-                    workspace_bytes >= ft3d_conv_os_workspace(ncols, scratch_slots)),
-               "ft3d_conv_os: needs a 256-byte aligned workspace of ft3d_conv_os_workspace(ncols, slots) bytes");
+                    workspace_bytes >= ft3d_conv_os_workspace(ncols, scratch_slots, tile_rows)),
+               "ft3d_conv_os: needs a 256-byte aligned workspace of ft3d_conv_os_workspace(ncols, slots, tile_rows) bytes");
   FT3D_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "ft3d_conv_os: running stats go together");
   OsArgs a;
   a.in = (const __nv_bfloat16*)in_bf16;
@@ -548,6 +591,8 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
   a.unit_cap = (int)unit_cap; a.K = K; a.kflip = kflip; a.red = red; a.ncols = ncols;
   a.tcols = os_tmem_cols(ncols);
   a.nbuf = 2 * a.tcols <= 512 ? 2 : 1;
+  a.cs = tile_rows / tc::kTileRows;
+  a.tile_rows = tile_rows;
   const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes;
   const int fixed = 4 * kOsStageFloats * (int)sizeof(float) + 8 * ncols * (int)sizeof(float) + (int)sizeof(OsHeader) + 1024 + 64;
   int nslots = (227 * 1024 - fixed) / stage_bytes;
@@ -555,9 +600,11 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
   FT3D_REQUIRE(nslots >= 2, "ft3d_conv_os: red=%d ncols=%d does not fit shared memory", red, ncols);
   a.nslots = nslots;
   const int smem_bytes = fixed + nslots * stage_bytes;
-  const unsigned grid = (unsigned)(tiles < kOsMaxCtas ? tiles : kOsMaxCtas);
+  const int64_t max_clusters = kOsMaxCtas / a.cs;
+  const unsigned grid = (unsigned)((tiles < max_clusters ? tiles : max_clusters) * a.cs);
   CUtensorMap tm;
   const bool tma = os_gather_mode() == 1;
+  FT3D_REQUIRE(tma || a.cs == 1, "ft3d_conv_os: cluster schedules (tile_rows > 128) need the TMA gather mode");
   if (tma) {
     int rc = make_row_tmap(&tm, in_bf16, n_in, red);
     if (rc) return rc;
@@ -571,10 +618,27 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
     configured = 1;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (tma)
+  if (a.cs > 1) {                  // thread-block clusters: the CTAs of a cluster share every B block (multicast)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kOsThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, conv_os_kernel<true>, tm, a);
+  } else if (tma) {
     launch_pdl(conv_os_kernel<true>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
-  else
+  } else {
     launch_pdl(conv_os_kernel<false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
+  }
   int nparts = (int)grid;
   if (scratch_slots > 0) {                       // the schedule has split tiles: fold their unit partials
     const int fgrid = (int)os_fold_ctas(scratch_slots);
@@ -585,10 +649,10 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
     float* fparts = stats ? a.partials + (size_t)grid * 2 * ncols : nullptr;
     if (stats)
       launch_pdl(conv_os_fold_kernel<true>, dim3(fgrid), dim3(cv, ry), 0, s, (const int4*)split_tiles, num, out_row,
-                 (const float*)a.scratch, (int)ncols, out, fparts);
+                 (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
     else
       launch_pdl(conv_os_fold_kernel<false>, dim3(fgrid), dim3(cv, ry), 0, s, (const int4*)split_tiles, num, out_row,
-                 (const float*)a.scratch, (int)ncols, out, fparts);
+                 (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
     nparts += fgrid;
   }
   if (stats)

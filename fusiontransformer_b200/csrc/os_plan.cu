@@ -22,7 +22,7 @@
 
 namespace ft3d {
 
-constexpr int kOsTile = 128;
+constexpr int kOsTile = 128;        // rows of one CTA tile; a schedule tile is tile_rows = 128 x (CTAs of a cluster)
 
 // masks + per-offset occupancy counts.  A warp owns 32/kpad rows per iteration; lane -> (row sub, offset k).
 __global__ void os_mask_kernel(const int32_t* __restrict__ table, int64_t n_rows, int K, int kpad,
@@ -84,16 +84,15 @@ __global__ void os_key_kernel(const uint32_t* __restrict__ mask, int64_t n_rows,
 
 // one warp per tile: union of the masks of its 128 sorted rows
 __global__ void os_tile_union_kernel(const int32_t* __restrict__ sorted_rows, const uint32_t* __restrict__ mask,
-                                     int64_t n_rows, int T, uint32_t* __restrict__ tile_union) {
+                                     int64_t n_rows, int T, int tile_rows, uint32_t* __restrict__ tile_union) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t t = warp0; t < T; t += nwarps) {
     uint32_t u = 0;
-#pragma unroll
-    for (int i = 0; i < kOsTile / 32; ++i) {
-      const int64_t s = t * kOsTile + i * 32 + lane;
+    for (int i = 0; i < tile_rows / 32; ++i) {
+      const int64_t s = t * tile_rows + i * 32 + lane;
       if (s < n_rows) u |= __ldg(mask + __ldg(sorted_rows + s));
     }
 #pragma unroll
@@ -198,7 +197,7 @@ os_tile_scan_kernel(const uint32_t* __restrict__ tile_union, int T, int grid_cta
 
 // one CTA (128 threads) per tile: slot r -> output row, per pass the gather index of the slot, and the tile's units
 //   unit = {first pass, passes, tile, chunks of the tile, chunk index, first scratch slot of the tile, 0, 0}
-__global__ void __launch_bounds__(kOsTile)
+__global__ void __launch_bounds__(4 * kOsTile)
 os_emit_kernel(const int32_t* __restrict__ table, int kpad, const int32_t* __restrict__ sorted_rows, int64_t n_rows,
                const uint32_t* __restrict__ tile_union, const int4* __restrict__ tile_info,
                const int32_t* __restrict__ split_idx, const int32_t* __restrict__ num, int64_t pass_cap,
@@ -206,8 +205,8 @@ os_emit_kernel(const int32_t* __restrict__ table, int kpad, const int32_t* __res
                int32_t* __restrict__ pass_k, int32_t* __restrict__ pass_idx, int32_t* __restrict__ units,
                uint32_t* __restrict__ unit_key, int32_t* __restrict__ unit_id) {
   pdl_enter();
-  const int t = blockIdx.x, r = threadIdx.x;
-  const int64_t s = (int64_t)t * kOsTile + r;
+  const int t = blockIdx.x, r = threadIdx.x, tile_rows = blockDim.x;
+  const int64_t s = (int64_t)t * tile_rows + r;
   const int row = s < n_rows ? __ldg(sorted_rows + s) : -1;
   out_row[s] = row;
   uint32_t u = tile_union[t];
@@ -218,7 +217,7 @@ os_emit_kernel(const int32_t* __restrict__ table, int kpad, const int32_t* __res
     u &= u - 1;
     if (p < pass_cap) {                 // the caller sized the arrays from an upper bound; never write past it
       if (r == 0) pass_k[p] = k;
-      pass_idx[p * kOsTile + r] = row >= 0 ? __ldg(table + (int64_t)row * kpad + k) : -1;
+      pass_idx[p * tile_rows + r] = row >= 0 ? __ldg(table + (int64_t)row * kpad + k) : -1;
     }
     ++p;
   }
@@ -280,7 +279,7 @@ struct OsPlanWs {
   size_t total;
 };
 
-static OsPlanWs os_carve(void* ws, int64_t n, int64_t unit_cap) {
+static OsPlanWs os_carve(void* ws, int64_t n, int64_t unit_cap) {     // sized for the smallest tile (128 rows)
   OsPlanWs w;
   char* p = (char*)ws;
   const size_t n4 = align_up((size_t)(n > 0 ? n : 1) * 4, 256);
@@ -322,8 +321,9 @@ extern "C" {
 
 size_t ft3d_conv_os_plan_workspace(int64_t n_rows, int64_t unit_cap) { return os_carve(nullptr, n_rows, unit_cap).total; }
 
-int ft3d_conv_os_plan(const int32_t* table, int64_t n_rows, int32_t K, int32_t kpad, int64_t pass_cap,
-                      int64_t unit_cap, int32_t chunk_passes, int32_t* units_out, int32_t* split_tiles_out,
+int ft3d_conv_os_plan(const int32_t* table, int64_t n_rows, int32_t K, int32_t kpad, int32_t tile_rows,
+                      int64_t pass_cap, int64_t unit_cap, int32_t chunk_passes, int32_t* units_out,
+                      int32_t* split_tiles_out,
                       int32_t* out_row_out, int32_t* pass_k_out, int32_t* pass_idx_out, int32_t* num_out,
                       void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
@@ -335,12 +335,14 @@ int ft3d_conv_os_plan(const int32_t* table, int64_t n_rows, int32_t K, int32_t k
   FT3D_REQUIRE(table && units_out && split_tiles_out && out_row_out && pass_k_out && pass_idx_out && workspace,
                "ft3d_conv_os_plan: null argument");
   FT3D_REQUIRE(K > 0 && K <= kpad && (kpad == 8 || kpad == 16 || kpad == 32) && pass_cap > 0 && unit_cap > 0 &&
-                   n_rows < (1ll << 31) && chunk_passes >= 0 && chunk_passes <= 32,
+                   n_rows < (1ll << 31) && chunk_passes >= 0 && chunk_passes <= 32 &&
+                   (tile_rows == 128 || tile_rows == 256 || tile_rows == 512),
                "ft3d_conv_os_plan: bad arguments");
   OsPlanWs w = os_carve(workspace, n_rows, unit_cap);
   FT3D_REQUIRE(((uintptr_t)workspace & 255) == 0 && workspace_bytes >= w.total,
                "ft3d_conv_os_plan: workspace too small (%zu < %zu) or not 256-byte aligned", workspace_bytes, w.total);
-  const int T = (int)((n_rows + kOsTile - 1) / kOsTile);
+  const int T = (int)((n_rows + tile_rows - 1) / tile_rows);
+  const int clusters = kNumSMs / (tile_rows / kOsTile);            // work units are dealt to CTA clusters
   launch_pdl(os_zero_kernel, dim3(1), dim3(32), 0, s, w.counts, 32);
   launch_pdl(os_mask_kernel, dim3(grid_for(n_rows * kpad, 256)), dim3(256), 0, s, table, n_rows, (int)K, (int)kpad,
              w.mask, w.counts);
@@ -351,11 +353,11 @@ int ft3d_conv_os_plan(const int32_t* table, int64_t n_rows, int32_t K, int32_t k
   FT3D_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, (const uint32_t*)w.key, w.key_sorted,
                                             (const int32_t*)w.row_id, w.sorted_rows, (int)n_rows, 0, (int)K, s));
   launch_pdl(os_tile_union_kernel, dim3(grid_for((int64_t)T * 32, 256)), dim3(256), 0, s,
-             (const int32_t*)w.sorted_rows, (const uint32_t*)w.mask, n_rows, T, w.tile_union);
+             (const int32_t*)w.sorted_rows, (const uint32_t*)w.mask, n_rows, T, (int)tile_rows, w.tile_union);
   launch_pdl(os_tile_scan_kernel, dim3(1), dim3(1024), 0, s, (const uint32_t*)w.tile_union, T,
-             T < kNumSMs ? T : kNumSMs, (int)chunk_passes, w.tile_info, w.split_idx, num_out);
+             T < clusters ? T : clusters, (int)chunk_passes, w.tile_info, w.split_idx, num_out);
   launch_pdl(os_fill_u32_kernel, dim3(grid_for(unit_cap, 256)), dim3(256), 0, s, w.unit_key, unit_cap, 0xFFFFFFFFu);
-  launch_pdl(os_emit_kernel, dim3((unsigned)T), dim3(kOsTile), 0, s, table, (int)kpad, (const int32_t*)w.sorted_rows,
+  launch_pdl(os_emit_kernel, dim3((unsigned)T), dim3((unsigned)tile_rows), 0, s, table, (int)kpad, (const int32_t*)w.sorted_rows,
              n_rows, (const uint32_t*)w.tile_union, (const int4*)w.tile_info, (const int32_t*)w.split_idx,
              (const int32_t*)num_out, pass_cap, unit_cap, (int64_t)T, split_tiles_out, out_row_out, pass_k_out,
              pass_idx_out, w.units, w.unit_key, w.unit_id);

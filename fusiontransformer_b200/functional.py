@@ -101,7 +101,7 @@ class KernelMap:
         self._event = None
         self._num_pairs = None
         self.aux = {}               # per-map caches owned by the conv kernels (tile schedules, ...)
-        self._os = {}               # side ("out" | "in") -> ops.OsPlan of the output-stationary convolution
+        self._os = {}               # (side, tile_rows) -> ops.OsPlan of the output-stationary convolution
 
     @property
     def nbrT(self):
@@ -142,31 +142,31 @@ class KernelMap:
                                                   self.n_in, self.num_pairs())
         return self._pposT
 
-    def os_plan(self, side: str):
+    def os_plan(self, side: str, tile_rows: int = 128):
         """Tile schedule of conv_os for the rows of one side of the map: ``"out"`` = the map's output rows (forward
         conv, dgrad of a transposed conv; table ``nbr``), ``"in"`` = its input rows (dgrad, transposed conv; table
         ``nbrT``).  A symmetric stride-1 map (nbrT[i,k] == nbr[i,K-1-k]) serves both sides with the "out" schedule
         and mirrored weights (``kflip``)."""
-        plan = self._os.get(side)
+        plan = self._os.get((side, tile_rows))
         if plan is None:
             table = self.nbr if side == "out" else self.nbrT
-            plan = ops.conv_os_plan(table, self.K, self._num_pairs)
-            self._os[side] = plan
+            plan = ops.conv_os_plan(table, self.K, self._num_pairs, tile_rows)
+            self._os[(side, tile_rows)] = plan
         return plan
 
-    def os_args(self, role: str):
+    def os_args(self, role: str, tile_rows: int = 128):
         """-> (plan, w_transposed, kflip, n_rows) of a convolution role (forward | dgrad | transposed |
         dgrad_transposed)."""
         if role == "forward":
-            return self.os_plan("out"), False, False, self.n_out
+            return self.os_plan("out", tile_rows), False, False, self.n_out
         if role == "dgrad":
             if self.symmetric:
-                return self.os_plan("out"), True, True, self.n_in
-            return self.os_plan("in"), True, False, self.n_in
+                return self.os_plan("out", tile_rows), True, True, self.n_in
+            return self.os_plan("in", tile_rows), True, False, self.n_in
         if role == "transposed":
-            return self.os_plan("in"), False, False, self.n_in
+            return self.os_plan("in", tile_rows), False, False, self.n_in
         if role == "dgrad_transposed":
-            return self.os_plan("out"), True, False, self.n_out
+            return self.os_plan("out", tile_rows), True, False, self.n_out
         raise ValueError(role)
 
     def host_offsets(self):

@@ -123,23 +123,24 @@ class StaticGeometry:
             skm._offsets = slot(key + ".offsets", km.K + 1, (), torch.int32, 0)
             if self.use_os:
                 # tile schedules of the output-stationary convolution, padded with empty tiles / passes
-                for side, op in km._os.items():
+                skm.os_cluster = getattr(km, "os_cluster", 1)
+                for (side, trows), op in km._os.items():
                     rows = self.row_caps[s_out] if side == "out" else self.row_caps[s_in]
-                    tcap = (rows + 127) // 128
-                    name = "%s.os_%s" % (key, side)
+                    tcap = (rows + trows - 1) // trows
+                    name = "%s.os_%s%d" % (key, side, trows)
                     n_pass, n_unit, n_slot = op.host_counts()[:3]
                     old = prev.pass_caps.get(name, (0, 0, 0)) if prev is not None else (0, 0, 0)
                     pcap, ucap, scap = (max(int(n_pass * 1.25) + 8, old[0]), max(int(n_unit * 1.25) + 8, tcap, old[1]),
                                         max(int(n_slot * 1.5) + 8, old[2]))
                     self.pass_caps[name] = (pcap, ucap, scap)
                     # `num` carries the batch's real unit count: the kernel never walks the padding units
-                    skm._os[side] = ops.OsPlan(slot(name + ".units", ucap, (8,), torch.int32, 0),
-                                               slot(name + ".split", tcap, (4,), torch.int32, 0),
-                                               slot(name + ".num", 8, (), torch.int32, 0),
-                                               slot(name + ".out_row", tcap * 128, (), torch.int32, -1),
-                                               slot(name + ".pass_k", pcap, (), torch.int32, 0),
-                                               slot(name + ".pass_idx", pcap, (128,), torch.int32, -1),
-                                               rows, km.K, counts=(pcap, ucap, scap, 0, 0))
+                    skm._os[(side, trows)] = ops.OsPlan(slot(name + ".units", ucap, (8,), torch.int32, 0),
+                                                        slot(name + ".split", tcap, (4,), torch.int32, 0),
+                                                        slot(name + ".num", 8, (), torch.int32, 0),
+                                                        slot(name + ".out_row", tcap * trows, (), torch.int32, -1),
+                                                        slot(name + ".pass_k", pcap, (), torch.int32, 0),
+                                                        slot(name + ".pass_idx", pcap, (trows,), torch.int32, -1),
+                                                        rows, km.K, counts=(pcap, ucap, scap, 0, 0), tile_rows=trows)
             else:
                 skm._ppos = slot(key + ".ppos", self.row_caps[s_out], (kpad,), torch.int32, -1)
                 skm._pposT = slot(key + ".pposT", self.row_caps[s_in], (kpad,), torch.int32, -1)
@@ -181,9 +182,9 @@ class StaticGeometry:
             if self.use_os:
                 if set(km._os) != set(self.kernel_maps[key]._os):
                     return False
-                for side, op in km._os.items():
+                for (side, trows), op in km._os.items():
                     n_pass, n_unit, n_slot = op.host_counts()[:3]
-                    pcap, ucap, scap = self.pass_caps["%s.os_%s" % (key, side)]
+                    pcap, ucap, scap = self.pass_caps["%s.os_%s%d" % (key, side, trows)]
                     if n_pass > pcap or n_unit > ucap or n_slot > scap:
                         return False
         return True
@@ -211,8 +212,8 @@ class StaticGeometry:
             S[key + ".pairs"].load(km.pairs_padded[:L], copies, fills)
             S[key + ".offsets"].load(km.pair_offsets, copies, fills)
             if self.use_os:
-                for side, op in km._os.items():
-                    name = "%s.os_%s" % (key, side)
+                for (side, trows), op in km._os.items():
+                    name = "%s.os_%s%d" % (key, side, trows)
                     n_pass, n_unit = op.host_counts()[:2]
                     S[name + ".units"].load(op.units[:n_unit], copies, fills)
                     S[name + ".split"].load(op.split_tiles[:max(op.host_counts()[4], 1)], copies, fills)

@@ -434,12 +434,14 @@ class OsPlan:
     occupancy mask, the offsets ("passes") each tile visits with their gather indices, and the work units (tiles, or
     pass ranges of heavy tiles) in longest-first order."""
 
-    __slots__ = ("units", "split_tiles", "num", "out_row", "pass_k", "pass_idx", "T", "n_rows", "K", "counts")
+    __slots__ = ("units", "split_tiles", "num", "out_row", "pass_k", "pass_idx", "T", "n_rows", "K", "counts",
+                 "tile_rows")
 
-    def __init__(self, units, split_tiles, num, out_row, pass_k, pass_idx, n_rows, K, counts=None):
+    def __init__(self, units, split_tiles, num, out_row, pass_k, pass_idx, n_rows, K, counts=None, tile_rows=128):
         self.units, self.split_tiles, self.num = units, split_tiles, num
         self.out_row, self.pass_k, self.pass_idx = out_row, pass_k, pass_idx
-        self.T, self.n_rows, self.K = out_row.shape[0] // 128, n_rows, K
+        self.tile_rows = tile_rows      # 128 x CTAs of the cluster that shares a tile's weight blocks
+        self.T, self.n_rows, self.K = out_row.shape[0] // tile_rows, n_rows, K
         self.counts = counts            # host copy of num[:5] = (passes, units, scratch slots, cap, split tiles)
 
     def host_counts(self):
@@ -462,12 +464,12 @@ class OsPlan:
         return [self.units, self.split_tiles, self.num, self.out_row, self.pass_k, self.pass_idx]
 
 
-def conv_os_plan(table: torch.Tensor, k: int, max_pairs: int | None = None) -> OsPlan:
+def conv_os_plan(table: torch.Tensor, k: int, max_pairs: int | None = None, tile_rows: int = 128) -> OsPlan:
     """``table`` int32 [n_rows, kpad]: the neighbour table seen from the rows the convolution PRODUCES."""
     table = _chk(table, torch.int32, "table")
     n_rows, kpad = table.shape
     dev = table.device
-    T = (n_rows + 127) // 128
+    T = (n_rows + tile_rows - 1) // tile_rows
     cap = max(T * k, 1)
     if max_pairs is not None:
         cap = max(min(cap, int(max_pairs)), 1)         # every pass holds at least one pair
@@ -475,15 +477,15 @@ def conv_os_plan(table: torch.Tensor, k: int, max_pairs: int | None = None) -> O
     ucap = 4 * T                                       # a tile is split into at most 4 units
     units = torch.empty((ucap, 8), dtype=torch.int32, device=dev)
     split_tiles = torch.empty((max(T, 1), 4), dtype=torch.int32, device=dev)
-    out_row = torch.empty(T * 128, dtype=torch.int32, device=dev)
+    out_row = torch.empty(T * tile_rows, dtype=torch.int32, device=dev)
     pass_k = torch.empty(cap, dtype=torch.int32, device=dev)
-    pass_idx = torch.empty((cap, 128), dtype=torch.int32, device=dev)
+    pass_idx = torch.empty((cap, tile_rows), dtype=torch.int32, device=dev)
     num = torch.empty(8, dtype=torch.int32, device=dev)
     ws = _ws(lib().conv_os_plan_workspace(n_rows, ucap), dev)
-    lib().conv_os_plan(table.data_ptr(), n_rows, k, kpad, cap, ucap, chunk, units.data_ptr(), split_tiles.data_ptr(),
-                       out_row.data_ptr(), pass_k.data_ptr(), pass_idx.data_ptr(), num.data_ptr(), ws.data_ptr(),
-                       ws.numel(), _stream())
-    return OsPlan(units, split_tiles, num, out_row, pass_k, pass_idx, n_rows, k)
+    lib().conv_os_plan(table.data_ptr(), n_rows, k, kpad, tile_rows, cap, ucap, chunk, units.data_ptr(),
+                       split_tiles.data_ptr(), out_row.data_ptr(), pass_k.data_ptr(), pass_idx.data_ptr(), num.data_ptr(),
+                       ws.data_ptr(), ws.numel(), _stream())
+    return OsPlan(units, split_tiles, num, out_row, pass_k, pass_idx, n_rows, k, tile_rows=tile_rows)
 
 
 _OS_SCRATCH = {}
@@ -522,14 +524,15 @@ def conv_os(x16, plan: OsPlan, w, w_transposed: bool, kflip: bool, n_out: int, o
         eps, momentum, rm, rv = bn
         stat = torch.empty((2, ncols), dtype=torch.float32, device=dev)
     slots = plan.scratch_slots() if scratch_slots is None else scratch_slots
-    ws = os_scratch(dev, lib().conv_os_workspace(ncols, slots))
+    ws = os_scratch(dev, lib().conv_os_workspace(ncols, slots, plan.tile_rows))
     trace = None
     if OS_TRACE is not None:
-        trace = torch.zeros((min(plan.T, 148), 8), dtype=torch.int64, device=dev)
+        trace = torch.zeros((148, 8), dtype=torch.int64, device=dev)
         OS_TRACE.append(trace)
     lib().conv_os(x16.data_ptr(), x16.shape[0], plan.units.data_ptr(), plan.split_tiles.data_ptr(),
                   plan.num.data_ptr(), plan.out_row.data_ptr(),
-                  plan.pass_k.data_ptr(), plan.pass_idx.data_ptr(), plan.units.shape[0], plan.T, slots, plan.K,
+                  plan.pass_k.data_ptr(), plan.pass_idx.data_ptr(), plan.units.shape[0], plan.T, plan.tile_rows, slots,
+                  plan.K,
                   int(kflip), red, ncols, img.data_ptr(), out.data_ptr(), n_out, _valid(n_out), float(eps),
                   float(momentum), _p(stat), _p(rm), _p(rv), ws.data_ptr(), ws.numel(), _p(trace), _stream())
     return out, stat

@@ -19,7 +19,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import ops
+from . import conv_engine, ops
 from .functional import KernelMap, build_kernel_map, spdownsample
 from .ops import CoordTable
 
@@ -66,9 +66,10 @@ def _force(km: KernelMap, need_nbrT: bool):
     from . import conv_engine
     km.num_pairs()              # pairs, offsets, ppos + the single host read of this map
     if conv_engine.mode() == "tc" and conv_engine.os_enabled():
-        km.os_plan("out")       # tile schedules of the output-stationary convolution (forward / dgrad sides)
+        trows = conv_engine.os_tile_rows(km, 0, 0)
+        km.os_plan("out", trows)       # tile schedules of the output-stationary convolution (forward / dgrad sides)
         if not km.symmetric:
-            km.os_plan("in")
+            km.os_plan("in", trows)
     else:
         km.pposT
     if need_nbrT:
@@ -90,6 +91,7 @@ def build_plan(coords: torch.Tensor, strides=(1, 2, 4, 8, 16), v2p_strides=(1, 1
     plan.tables[s] = CoordTable(plan.sparse_hash)
     for nxt in strides[1:] + (None,):
         km3 = build_kernel_map(c, c, 3, s, plan.tables[s])
+        km3.os_cluster = conv_engine.os_cluster_for_stride(s)
         plan.kernel_maps["k3_os%d_s1_d1" % s] = km3
         _force(km3, need_nbrT=fp32_layers)
         if nxt is None:

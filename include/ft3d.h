@@ -208,12 +208,13 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
  *   ft3d_conv_os_plan : schedule of one side of a kernel map.  table int32 [n_rows,kpad] is the neighbour table
  *       seen from the rows being PRODUCED (nbr of ft3d_kmap_build for a forward conv, its transpose for dgrad /
  *       transposed conv).  Rows are sorted by occupancy mask (rarest offsets most significant) into T =
- *       ceil(n_rows/128) tiles; the offsets that occur in a tile are its passes.  A tile with more than `cap`
+ *       ceil(n_rows/tile_rows) tiles (tile_rows = 128, 256 or 512 = 128 x the CTAs of the thread-block cluster that
+ *       will share a tile's weight blocks); the offsets that occur in a tile are its passes.  A tile with more than `cap`
  *       passes is split into ceil(passes/cap) work units over disjoint pass ranges (cap = chunk_passes, or, if 0,
  *       ~3/4 of the mean passes per CTA clamped to [4,8]); units are listed longest first.  Outputs:
  *       units_out int32 [unit_cap,8] = {first pass, passes, tile, units of the tile, index among them, first scratch
- *       slot of the tile, 0, 0}; out_row_out int32 [T*128] (row of each tile slot, -1 = empty); pass_k_out int32
- *       [pass_cap]; pass_idx_out int32 [pass_cap,128] (gather row per slot, -1 = none); split_tiles_out int32 [T,4] =
+ *       slot of the tile, 0, 0}; out_row_out int32 [T*tile_rows] (row of each tile slot, -1 = empty); pass_k_out int32
+ *       [pass_cap]; pass_idx_out int32 [pass_cap,tile_rows] (gather row per slot, -1 = none); split_tiles_out int32 [T,4] =
  *       {tile, its units, its first scratch slot, 0} for the tiles that were split; num_out int32 [8] = {P passes,
  *       U units, S scratch slots (units of split tiles), cap, split tiles, 0, 0, 0}.  P <= min(pairs, T*K), U <= 4T
  *       (a tile is split evenly into at most 4 units); entries beyond pass_cap / unit_cap are dropped, so the caller
@@ -224,23 +225,26 @@ int ft3d_conv_wgrad_pairs_tc(const void* a_bf16, const void* b_bf16, const int32
  *       units of a split tile leave partial tiles in scratch slots and a second, tiny launch (one CTA per split
  *       tile) adds them in unit order, so the result is bit-identical from launch to launch.  in_bf16 [n_in,red]; wpacked as for ft3d_conv_pairs_tc
  *       (ft3d_conv_pack_weights); kflip != 0 uses B_{K-1-k} (dgrad of a symmetric stride-1 map re-uses the forward
- *       schedule).  valid_rows (nullable): out holds n_out rows of which the first *valid_rows are real; the others
+ *       schedule).  tile_rows > 128 launches clusters of tile_rows/128 CTAs that walk a tile's passes in lockstep: rank
+ *       0 multicasts each weight block B_k to all of them (one L2 read per cluster instead of one per 128 rows).
+ *       valid_rows (nullable): out holds n_out rows of which the first *valid_rows are real; the others
  *       are zero-filled.  stat != NULL: BatchNorm training statistics of the rows written (semantics of
  *       ft3d_bn_stats: stat [2,ncols] = mean, rstd; running stats updated) computed in the epilogue, deterministic
  *       (per-CTA partial rows folded in double by a third, tiny launch).  workspace (needed with statistics or
- *       scratch_slots > 0): ft3d_conv_os_workspace(ncols, scratch_slots) bytes, 256-byte aligned, private to the
+ *       scratch_slots > 0): ft3d_conv_os_workspace(ncols, scratch_slots, tile_rows) bytes, 256-byte aligned, private to the
  *       stream.  trace (nullable): 8 x uint64 per CTA of device timestamps (tools/conv_os_probe.py).
  *   Gathers are TMA (cp.async.bulk.tensor tile::gather4); FT3D_OS_GATHER=ldgsts selects 16-byte cp.async. */
 size_t ft3d_conv_os_plan_workspace(int64_t n_rows, int64_t unit_cap);
-int ft3d_conv_os_plan(const int32_t* table, int64_t n_rows, int32_t K, int32_t kpad, int64_t pass_cap,
-                      int64_t unit_cap, int32_t chunk_passes, int32_t* units_out, int32_t* split_tiles_out,
+int ft3d_conv_os_plan(const int32_t* table, int64_t n_rows, int32_t K, int32_t kpad, int32_t tile_rows,
+                      int64_t pass_cap, int64_t unit_cap, int32_t chunk_passes, int32_t* units_out,
+                      int32_t* split_tiles_out,
                       int32_t* out_row_out, int32_t* pass_k_out, int32_t* pass_idx_out, int32_t* num_out,
                       void* workspace, size_t workspace_bytes, ft3d_stream_t stream);
-size_t ft3d_conv_os_workspace(int32_t ncols, int64_t scratch_slots);
+size_t ft3d_conv_os_workspace(int32_t ncols, int64_t scratch_slots, int32_t tile_rows);
 int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const int32_t* split_tiles,
                  const int32_t* num, const int32_t* out_row, const int32_t* pass_k, const int32_t* pass_idx,
-                 int64_t unit_cap, int64_t tiles, int64_t scratch_slots, int32_t K, int32_t kflip, int32_t red,
-                 int32_t ncols, const void* wpacked, float* out, int64_t n_out, const int32_t* valid_rows, float eps,
+                 int64_t unit_cap, int64_t tiles, int32_t tile_rows, int64_t scratch_slots, int32_t K, int32_t kflip,
+                 int32_t red, int32_t ncols, const void* wpacked, float* out, int64_t n_out, const int32_t* valid_rows, float eps,
                  float momentum, float* stat, float* running_mean, float* running_var, void* workspace,
                  size_t workspace_bytes, void* trace, ft3d_stream_t stream);
 

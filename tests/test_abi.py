@@ -36,12 +36,16 @@ def test_host_only_entry_points():
     assert L.unique_workspace(1000) > 1000 * 8
     # argument validation happens before any CUDA call, so it is testable without a GPU
     with pytest.raises(_lib.Ft3dError, match="bad arguments"):          # K > 32
-        L.conv_os(256, 10, 256, 256, 256, 256, 256, 256, 8, 1, 0, 40, 0, 64, 64, 256, 256, 128, None, 0.0, 0.0, None,
+        L.conv_os(256, 10, 256, 256, 256, 256, 256, 256, 8, 1, 128, 0, 40, 0, 64, 64, 256, 256, 128, None, 0.0, 0.0, None,
                   None, None, None, 0, None, None)
     with pytest.raises(_lib.Ft3dError, match="unsupported shape"):      # red % 16 != 0
-        L.conv_os(256, 10, 256, 256, 256, 256, 256, 256, 8, 1, 0, 27, 0, 20, 64, 256, 256, 128, None, 0.0, 0.0, None,
+        L.conv_os(256, 10, 256, 256, 256, 256, 256, 256, 8, 1, 128, 0, 27, 0, 20, 64, 256, 256, 128, None, 0.0, 0.0, None,
                   None, None, None, 0, None, None)
-    assert L.conv_os_plan_workspace(1000, 32) > 5 * 1000 * 4 and L.conv_os_workspace(128, 4) >= 4 * 128 * 128 * 4
+    with pytest.raises(_lib.Ft3dError, match="bad arguments"):          # tile_rows must be 128 x {1, 2, 4}
+        L.conv_os(256, 10, 256, 256, 256, 256, 256, 256, 8, 1, 384, 0, 27, 0, 64, 64, 256, 256, 128, None, 0.0, 0.0, None,
+                  None, None, None, 0, None, None)
+    assert L.conv_os_plan_workspace(1000, 32) > 5 * 1000 * 4
+    assert L.conv_os_workspace(128, 4, 256) >= 4 * 256 * 128 * 4
 
 
 def test_no_cpu_fallback():

@@ -39,8 +39,9 @@ def _check_plan(plan, table, K):
     P, U, S, cap, NS = plan.host_counts()
     units, out_row = plan.units.cpu().numpy()[:U], plan.out_row.cpu().numpy()
     pass_k, pass_idx = plan.pass_k.cpu().numpy()[:P], plan.pass_idx.cpu().numpy()[:P]
-    T = (n + 127) // 128
-    assert out_row.shape == (T * 128,) and 1 <= cap <= 32
+    R = plan.tile_rows
+    T = (n + R - 1) // R
+    assert out_row.shape == (T * R,) and 1 <= cap <= 32 and pass_idx.shape[1] == R
     live = out_row[out_row >= 0]
     assert np.array_equal(np.sort(live), np.arange(n))                 # every row produced exactly once
     assert np.all(out_row[n:] == -1)                                   # empty slots only behind the last row
@@ -63,7 +64,7 @@ def _check_plan(plan, table, K):
         first, npass = int(us[0][0]), sum(int(un[1]) for un in us)
         for a, b in zip(us, us[1:]):
             assert int(b[0]) == int(a[0]) + int(a[1])                  # disjoint, consecutive pass ranges
-        rows = out_row[t * 128:(t + 1) * 128]
+        rows = out_row[t * R:(t + 1) * R]
         ok = rows >= 0
         union = np.flatnonzero(occ[rows[ok]].any(0))
         assert np.array_equal(pass_k[first:first + npass], union)      # ascending offsets, exactly the used ones
@@ -75,7 +76,7 @@ def _check_plan(plan, table, K):
     split = plan.split_tiles.cpu().numpy()[:NS]
     want = [(t, len(by_tile[t]), int(by_tile[t][0][5])) for t in range(T) if len(by_tile[t]) > 1]
     assert [tuple(int(v) for v in row[:3]) for row in split] == want     # split tiles listed in tile order
-    return pairs_seen / max(1, 128 * P)
+    return pairs_seen / max(1, R * P)
 
 
 def test_schedule_properties(ft, geom):
@@ -85,6 +86,10 @@ def test_schedule_properties(ft, geom):
     e2 = _check_plan(ops.conv_os_plan(km2.nbr, 8), km2.nbr, 8)
     eT = _check_plan(ops.conv_os_plan(km2.nbrT, 8), km2.nbrT, 8)
     assert e3 > 0.45 and eT > 0.9, (e3, e2, eT)       # mask sorting keeps the tiles dense (random order: ~0.15)
+    # cluster schedules: tiles of 256 / 512 rows shared by 2 / 4 CTAs
+    for trows in (256, 512):
+        _check_plan(ops.conv_os_plan(km3.nbr, 27, tile_rows=trows), km3.nbr, 27)
+        _check_plan(ops.conv_os_plan(km2.nbrT, 8, tile_rows=trows), km2.nbrT, 8)
     # deterministic: the same table gives the same schedule
     a, b = ops.conv_os_plan(km3.nbr, 27), ops.conv_os_plan(km3.nbr, 27)
     assert torch.equal(a.out_row, b.out_row) and torch.equal(a.units[:a.host_counts()[1]], b.units[:b.host_counts()[1]])
@@ -261,3 +266,34 @@ def test_wgrad_two_stage_is_deterministic_and_matches_atomic(ft, geom, monkeypat
     d0 = ops.conv_wgrad_pairs_tc(a16, b16, None, None, 1, 0, cin, cout, n)
     want = a16.float().t() @ b16.float()
     assert rel_l2(d0[0], want) < 1e-5
+
+
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("cin,cout", [(32, 32), (96, 128), (256, 256), (384, 256), (256, 384)])
+def test_conv_os_cluster_multicast_matches_single_cta(ft, geom, monkeypatch, cluster, cin, cout):
+    """Thread-block clusters of 2 / 4 CTAs share one schedule tile's weight blocks (multicast bulk copy, multicast
+    tcgen05.commit on the ring's empty barriers): same rows as the single-CTA kernel up to fp32 re-association of the
+    split-tile fold, deterministic, statistics included, forward and dgrad."""
+    from oracle import ts_ops as ts
+    from fusiontransformer_b200 import conv_engine, ops
+    monkeypatch.setattr(ts, "OPERAND_DTYPE", "bf16")
+    g = torch.Generator().manual_seed(cin + cout + cluster)
+    C = geom["Co"]
+    n = C.shape[0]
+    feats = torch.randn(n, cin, generator=g)
+    w = torch.randn(27, cin, cout, generator=g) / (cin * 27) ** 0.5
+    fo = feats.clone().requires_grad_(True)
+    yo = ts.conv3d(ts.SparseTensor(fo, C, 1), w, 3).F
+    gsel = torch.randn(yo.shape, generator=g)
+    (yo * gsel).sum().backward()
+    km, wg = geom["km3"], w.cuda()
+    x16, g16 = ops.to_bf16(feats.cuda()), ops.to_bf16(gsel.cuda())
+    monkeypatch.setenv("FT3D_OS_CLUSTER", "1")
+    y1, st1 = conv_engine.os_conv(x16, km, wg, "forward", bn=(1e-5, 0.1, None, None))
+    monkeypatch.setenv("FT3D_OS_CLUSTER", str(cluster))
+    outs = [conv_engine.os_conv(x16, km, wg, "forward", bn=(1e-5, 0.1, None, None)) for _ in range(3)]
+    assert rel_l2(outs[0][0], yo) < 5e-3 and rel_l2(outs[0][0], y1) < 1e-5 and rel_l2(outs[0][1], st1) < 1e-4
+    for y, st in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(st, outs[0][1])
+    gin, _ = conv_engine.os_conv(g16, km, wg, "dgrad")
+    assert rel_l2(gin, fo.grad) < 5e-3

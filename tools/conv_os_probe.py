@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--stats", type=int, default=1)
+    ap.add_argument("--cluster", type=int, default=1, help="CTAs per cluster sharing B (1, 2, 4)")
     ap.add_argument("--detail", action="store_true", help="per-CTA breakdown of the slowest CTAs")
     ap.add_argument("--only", default="", help="comma list of layer indices")
     a = ap.parse_args()
@@ -87,13 +88,15 @@ def main():
         g = torch.Generator(device=dev).manual_seed(cin * 7 + cout)
         x16 = ops.to_bf16(torch.randn(km.n_in, cin, device=dev, generator=g))
         w = torch.nn.Parameter(torch.randn(ks ** 3, cin, cout, device=dev, generator=g) * 0.05)
-        plan = km.os_plan("out")
+        os.environ["FT3D_OS_CLUSTER"] = str(a.cluster)
+        plan = km.os_plan("out", 128 * a.cluster)
         P, U, S, cap, NS = plan.host_counts()
         bn = (1e-5, 0.1, None, None) if a.stats else None
         t = {}
         for mode in ("tma", "ldgsts"):
             os.environ["FT3D_OS_GATHER"] = mode
-            t[mode] = graph_time(lambda: conv_engine.os_conv(x16, km, w, "forward", bn=bn))
+            t[mode] = (graph_time(lambda: conv_engine.os_conv(x16, km, w, "forward", bn=bn))
+                       if (mode == "tma" or a.cluster == 1) else float("nan"))
         os.environ["FT3D_OS_GATHER"] = "tma"
         km.ppos
         tp = graph_time(lambda: ops.conv_reduce_bn(conv_engine.pairs_partial(x16, km, w, "forward")[0], km.ppos, cout,
@@ -102,6 +105,7 @@ def main():
         conv_engine.os_conv(x16, km, w, "forward", bn=bn)
         torch.cuda.synchronize()
         tr = ops.OS_TRACE[0].cpu().numpy().astype(np.int64)
+        tr = tr[tr[:, 0] > 0]                    # CTAs that ran (the grid is min(tiles, 148))
         ops.OS_TRACE = None
         t0 = tr[:, 0]
         rel = lambda c: (tr[:, c] - t0) / 1e3
