@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--fmap-format", default="channels_last", choices=["channels_last", "nchw"],
                     help="memory format of the synthetic image-feature map the lift gathers from")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-baseline", action="store_true",
+                    help="at --gpus 1 with the default workload, skip the extra 1-GPU run of configs[2] (the workload "
+                         "every --gpus N > 1 run uses) that is reported as `scaling_baseline`")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--prefetch-thread", dest="no_prefetch_thread", action="store_false",
                     help="build the next batch's geometry from a worker thread (GIL-bound: slower)")
@@ -181,6 +184,7 @@ def main():
                     help="build each batch's geometry inside its own step (host reads stall the launch queue)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    default_workload = args.workload is None
     if args.workload is None:
         args.workload = "nuscenes" if args.gpus <= 1 else "kitti"
 
@@ -511,6 +515,25 @@ def main():
         for ms_, cnt, key in rows[:args.trace_top]:
             print("  %8.3f ms %6.1f x %7.1f us  %s" % (ms_, cnt, 1e3 * ms_ / max(cnt, 1e-9), key[:110]), file=sys.stderr)
 
+    # The data-parallel runs (--gpus 2/4/8) use configs[2] (KITTI-shaped); their single-GPU point is measured here, in
+    # a child process, so that the N = 1 line carries both the headline (configs[1]) and the scaling baseline.
+    scaling_baseline = None
+    if rank == 0 and world == 1 and default_workload and args.impl == "ours" and not args.no_scaling_baseline:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--gpus", "1", "--workload", "kitti",
+                                "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline",
+                                "--no-roofline", "--fusion", args.fusion, "--fmap-format", args.fmap_format],
+                               capture_output=True, text=True, timeout=600)
+            for ln in r.stdout.splitlines():
+                if ln.startswith("{"):
+                    d = json.loads(ln)
+                    scaling_baseline = {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"],
+                                        "ms_per_step": d["ms_per_step"], "e2e": d["e2e"], "n_gpus": 1,
+                                        "note": "same bench.py, --workload kitti --gpus 1: the single-GPU point of the "
+                                                "configs[2] scaling curve that --gpus 2/4/8 report"}
+        except Exception as e:  # noqa: BLE001
+            scaling_baseline = {"error": str(e)[:200]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sps, spstep, done = time_oracle(wl["shape"], steps=24, warmup=1, budget_s=15.0)
@@ -542,7 +565,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernel_ms_per_step": shares,
+            "kernel_ms_per_step": shares, "scaling_baseline": scaling_baseline,
         }
         print(json.dumps(line), flush=True)
     if pre is not None:
