@@ -112,6 +112,9 @@ class GradSync:
         view = self.flat[s:e]
         if self.overlap:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            from .fused import _BranchStream           # gradients of a bucket may have been produced on either stream
+            for idx in _BranchStream.used:
+                self.comm_stream.wait_stream(_BranchStream.streams[idx])
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(view, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group)
         else:

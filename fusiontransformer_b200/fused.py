@@ -58,7 +58,31 @@ class _SideStream:
         cls.keep.clear()
 
 
+class _BranchStream:
+    """The shortcut convolution of a ResidualBlock (kernel 1 conv + BatchNorm, models/spvcnn.py:69-75) does not depend
+    on the block's main branch: it runs on a second stream, forward and (autograd replays a node on its forward stream)
+    backward, and overlaps the main branch's conv chain.  ``FT3D_BRANCH_STREAM=0`` keeps everything on one stream."""
+    streams = {}
+    used = set()
+
+    @classmethod
+    def enabled(cls):
+        import os
+        return os.environ.get("FT3D_BRANCH_STREAM", "1") != "0"
+
+    @classmethod
+    def get(cls, device):
+        st = cls.streams.get(device.index)
+        if st is None:
+            st = cls.streams[device.index] = torch.cuda.Stream(device=device)
+        cls.used.add(device.index)
+        return st
+
+
 def join_side_streams():
+    for idx in list(_BranchStream.used):
+        torch.cuda.current_stream(idx).wait_stream(_BranchStream.streams[idx])
+    _BranchStream.used.clear()
     _SideStream.join()
 
 
@@ -394,6 +418,18 @@ def _residual_forward(self, x):
     if not (isinstance(x, SparseTensor) and x.F.is_cuda):
         return self.relu(self.net(x) + self.downsample(x))
     nm, dm = list(self.net), list(self.downsample)
+    if dm and _BranchStream.enabled():
+        main = torch.cuda.current_stream(x.F.device)
+        side = _BranchStream.get(x.F.device)
+        side.wait_stream(main)                       # x is ready
+        with torch.cuda.stream(side):
+            shortcut = conv_bn_act(x, dm[0], dm[1], False).F.contiguous()
+        h = conv_bn_act(x, nm[0], nm[1], True)
+        main.wait_stream(side)
+        # allocated on the side stream, read on the main stream: keep it referenced until the streams are joined at the
+        # end of the step so that the caching allocator cannot recycle it under the reader (same rule as the wgrad fork)
+        _SideStream.keep.append(shortcut)
+        return conv_bn_act(h, nm[3], nm[4], True, res=shortcut)
     h = conv_bn_act(x, nm[0], nm[1], True)
     shortcut = x.F if not dm else conv_bn_act(x, dm[0], dm[1], False).F
     return conv_bn_act(h, nm[3], nm[4], True, res=shortcut.contiguous())
