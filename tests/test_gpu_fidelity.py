@@ -116,14 +116,22 @@ def test_tc_mode_trains_like_fp32_mode(monkeypatch):
     steps = 200
     lf = _train_curve("f32", steps, monkeypatch)
     lt = _train_curve("tc", steps, monkeypatch)
-    # windowed means (the per-step loss of two chaotic trajectories differs; the curves must not)
+    # The two trajectories are chaotic (and the fp32 run itself differs from run to run through its atomics), so in the
+    # steep part of the descent -- the loss falls 5x per 20 steps -- a shift of three steps is a 25 % difference at a
+    # fixed step.  The curves are therefore compared by WHEN they reach a loss level, and pointwise only where that is
+    # meaningful: at the start (same weights) and at the end (both overfitted).
+    def first_below(curve, level):
+        sm = np.convolve(curve, np.ones(5) / 5, mode="valid")
+        idx = np.flatnonzero(sm < level)
+        return int(idx[0]) if len(idx) else len(curve)
+
     w = 20
-    mf = lf.reshape(-1, w).mean(1)
-    mt = lt.reshape(-1, w).mean(1)
-    rel = np.abs(mt - mf) / mf
-    print("\nloss, mean of each %d-step window\n  f32: %s\n  tc : %s\n  rel: %s" %
-          (w, np.round(mf, 4), np.round(mt, 4), np.round(rel, 4)))
-    assert lf[-w:].mean() < 0.5 * lf[:5].mean() and lt[-w:].mean() < 0.5 * lt[:5].mean()     # both train
-    # every window within 2 % of the fp32 curve, or within 2e-3 absolute once the fixed batch is overfitted and the
-    # loss itself is ~1e-3 (measured on B200: 0.2 % while the loss is O(1), 2.2 % at 0.07, then |diff| <= 5e-4)
-    assert np.all(np.abs(mt - mf) < 0.02 * mf + 2e-3), rel
+    mf, mt = lf.reshape(-1, w).mean(1), lt.reshape(-1, w).mean(1)
+    hits = [(lv, first_below(lf, lv), first_below(lt, lv)) for lv in (1.0, 0.3, 0.1, 0.03, 0.01)]
+    print("\nloss, mean of each %d-step window\n  f32: %s\n  tc : %s\n  steps to reach (level, f32, tc): %s" %
+          (w, np.round(mf, 4), np.round(mt, 4), hits))
+    assert lf[-w:].mean() < 0.01 * lf[:5].mean() and lt[-w:].mean() < 0.01 * lt[:5].mean()   # both train (>100x)
+    assert abs(mt[0] - mf[0]) < 0.02 * mf[0]                  # same start: first window within 2 %
+    for lv, sf, st in hits:
+        assert sf < steps and st < steps and abs(st - sf) <= max(6, 0.15 * sf), (lv, sf, st)
+    assert abs(mt[-1] - mf[-1]) < 0.25 * mf[-1] + 2e-4        # same plateau
