@@ -448,29 +448,35 @@ conv_os_fold_kernel(const int4* __restrict__ split_tiles, const int32_t* __restr
   __shared__ int s_rows[4 * kTileRows];
   const int ns = __ldg(num + 4);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  // blockIdx.y = slice of the tile's rows: the fold is a handful of independent loads per thread, so more CTAs per
+  // tile shorten it to ~one L2 round trip
+  const int rows_per_slice = tile_rows / (int)gridDim.y;
+  const int slice0 = (int)blockIdx.y * rows_per_slice;
   if ((int)blockIdx.x < ns) {
     const int4 sp = __ldg(split_tiles + blockIdx.x);       // {tile, units, first scratch slot, -}
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int r = tid; r < tile_rows; r += blockDim.x * blockDim.y) s_rows[r] = __ldg(out_row + (int64_t)sp.x * tile_rows + r);
+    for (int r = tid; r < rows_per_slice; r += blockDim.x * blockDim.y)
+      s_rows[r] = __ldg(out_row + (int64_t)sp.x * tile_rows + slice0 + r);
     __syncthreads();
     const int ch = threadIdx.x * 4;
     const float* p0 = scratch + (size_t)sp.z * tile_rows * ncols + ch;
     const size_t cstride = (size_t)tile_rows * ncols;
     constexpr int RB = 4;
-    for (int r0 = threadIdx.y; r0 < tile_rows; r0 += RB * blockDim.y) {
+    for (int r0 = threadIdx.y; r0 < rows_per_slice; r0 += RB * blockDim.y) {
       float4 x[RB][4];
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int r = r0 + i * blockDim.y;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          x[i][c] = (r < tile_rows && c < sp.y) ? __ldg(reinterpret_cast<const float4*>(p0 + c * cstride + (size_t)r * ncols))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[i][c] = (r < rows_per_slice && c < sp.y)
+                        ? __ldg(reinterpret_cast<const float4*>(p0 + c * cstride + (size_t)(slice0 + r) * ncols))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
         const int r = r0 + i * blockDim.y;
-        if (r >= tile_rows) break;
+        if (r >= rows_per_slice) break;
         const int row = s_rows[r];
         if (row < 0) continue;
         float4 acc = x[i][0];
@@ -485,7 +491,7 @@ conv_os_fold_kernel(const int4* __restrict__ split_tiles, const int32_t* __restr
       }
     }
   }
-  if (STATS) col_publish(s1, s2, partials, ncols, s_stage);
+  if (STATS) col_publish(s1, s2, partials + (size_t)blockIdx.y * gridDim.x * 2 * ncols, ncols, s_stage);
 }
 
 static int os_tmem_cols(int n) {
@@ -534,9 +540,10 @@ static int os_gather_mode() {      // 1 = TMA gather4 (default), 0 = LDGSTS; rea
 
 constexpr int kOsMaxCtas = kNumSMs;
 
+constexpr int kOsFoldSlices = 4;                 // CTAs per split tile in the fold kernel
 static int64_t os_fold_ctas(int64_t scratch_slots) { return (scratch_slots + 1) / 2; }     // a split tile has >= 2 units
 static size_t os_partials_bytes(int ncols, int64_t scratch_slots) {
-  return align_up((size_t)(kOsMaxCtas + os_fold_ctas(scratch_slots)) * 2 * (size_t)ncols * sizeof(float), 256);
+  return align_up((size_t)(kOsMaxCtas + kOsFoldSlices * os_fold_ctas(scratch_slots)) * 2 * (size_t)ncols * sizeof(float), 256);
 }
 
 }  // namespace ft3d
@@ -648,12 +655,12 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
     if (ry > 32) ry = 32;
     float* fparts = stats ? a.partials + (size_t)grid * 2 * ncols : nullptr;
     if (stats)
-      launch_pdl(conv_os_fold_kernel<true>, dim3(fgrid), dim3(cv, ry), 0, s, (const int4*)split_tiles, num, out_row,
-                 (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
+      launch_pdl(conv_os_fold_kernel<true>, dim3(fgrid, kOsFoldSlices), dim3(cv, ry), 0, s, (const int4*)split_tiles, num,
+                 out_row, (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
     else
-      launch_pdl(conv_os_fold_kernel<false>, dim3(fgrid), dim3(cv, ry), 0, s, (const int4*)split_tiles, num, out_row,
-                 (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
-    nparts += fgrid;
+      launch_pdl(conv_os_fold_kernel<false>, dim3(fgrid, kOsFoldSlices), dim3(cv, ry), 0, s, (const int4*)split_tiles,
+                 num, out_row, (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
+    nparts += fgrid * kOsFoldSlices;
   }
   if (stats)
     launch_pdl(col_finalize_kernel<0>, dim3(ncols / 4), dim3(kColThreads), 0, s, (const float*)a.partials, nparts,
