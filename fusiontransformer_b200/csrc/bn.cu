@@ -62,7 +62,7 @@ template <int RB>
 __global__ void __launch_bounds__(kColThreads)
 bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_per_cta, const float* __restrict__ stat,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ res,
-                int relu, float* __restrict__ z, __nv_bfloat16* __restrict__ z16,
+                int relu, float* __restrict__ z, __nv_bfloat16* __restrict__ z16, int64_t ldz,
                 const int32_t* __restrict__ valid_rows) {
   pdl_enter();
   const int64_t nv = effective_rows(n, valid_rows);
@@ -95,9 +95,10 @@ bn_apply_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_p
           o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
       }
-      if (z != nullptr) *reinterpret_cast<float4*>(z + row * channels + ch) = o;
+      // ldz: row pitch of the outputs (> channels when z is the left part of a concatenation buffer)
+      if (z != nullptr) *reinterpret_cast<float4*>(z + row * ldz + ch) = o;
       if (z16 != nullptr)
-        *reinterpret_cast<uint2*>(z16 + row * channels + ch) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        *reinterpret_cast<uint2*>(z16 + row * ldz + ch) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
   }
 }
@@ -122,7 +123,7 @@ template <int RB>
 __global__ void __launch_bounds__(kColThreads)
 bn_bwd_reduce_kernel(const float* __restrict__ gz, const float* __restrict__ y, const __nv_bfloat16* __restrict__ z16,
                      const float* __restrict__ z, int64_t n, int channels, int rows_per_cta,
-                     const float* __restrict__ stat, float* __restrict__ partials,
+                     const float* __restrict__ stat, float* __restrict__ partials, int64_t ldg,
                      const int32_t* __restrict__ valid_rows) {
   pdl_enter();
   __shared__ float4 s_stage[kColStageFloat4];
@@ -138,9 +139,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ gz, const float* __restrict__ y, 
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
       const int64_t rr = r + i * rstep < row1 ? r + i * rstep : r;     // tail lanes re-read row r and are discarded
-      const int64_t off = rr * channels + ch;
-      g[i] = masked_grad(gz, z16, z, off);
-      v[i] = ld4(y + off);
+      g[i] = masked_grad(gz, z16, z, rr * ldg + ch);                    // ldg: row pitch of gz and of the saved output
+      v[i] = ld4(y + rr * channels + ch);
     }
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kColThreads)
 bn_bwd_apply_kernel(const float* __restrict__ gz, const float* __restrict__ y, const __nv_bfloat16* __restrict__ z16,
                     const float* __restrict__ z, int64_t n, int channels, int rows_per_cta,
                     const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ red,
-                    float* __restrict__ gy, __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres,
+                    float* __restrict__ gy, __nv_bfloat16* __restrict__ gy16, float* __restrict__ gres, int64_t ldg,
                     const int32_t* __restrict__ valid_rows) {
   pdl_enter();
   const int64_t nv = effective_rows(n, valid_rows);
@@ -180,9 +180,8 @@ bn_bwd_apply_kernel(const float* __restrict__ gz, const float* __restrict__ y, c
     for (int i = 0; i < RB; ++i) {
       const int64_t row = r + i * rstep;
       const int64_t rr = (row < row1 && row < nv) ? row : (r < nv ? r : 0);   // dead lanes re-read a live row
-      const int64_t off = rr * channels + ch;
-      g[i] = masked_grad(gz, z16, z, off);
-      v[i] = red != nullptr ? ld4(y + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[i] = masked_grad(gz, z16, z, rr * ldg + ch);
+      v[i] = red != nullptr ? ld4(y + rr * channels + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
@@ -204,6 +203,27 @@ bn_bwd_apply_kernel(const float* __restrict__ gz, const float* __restrict__ y, c
       if (gy != nullptr) *reinterpret_cast<float4*>(gy + off) = o;
       if (gy16 != nullptr) *reinterpret_cast<uint2*>(gy16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       if (gres != nullptr) *reinterpret_cast<float4*>(gres + off) = gg;
+    }
+  }
+}
+
+// dst[row, col0 + c] = src[row, c] for the fp32 tensor and (optionally) its bf16 copy: the skip half of
+// torchsparse.cat([deconv(y), skip]) (models/spvcnn.py:212-228) written next to the half bn_apply wrote in place
+__global__ void copy_cols_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ src16, int64_t n, int c,
+                                 float* __restrict__ dst, __nv_bfloat16* __restrict__ dst16, int64_t ld, int col0) {
+  pdl_enter();
+  const int c4 = c >> 2;
+  const int64_t total = n * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / c4;
+    const int q = (int)(i - row * c4) * 4;
+    const float4 v = ld4(src + row * c + q);
+    *reinterpret_cast<float4*>(dst + row * ld + col0 + q) = v;
+    if (dst16 != nullptr) {
+      uint2 h;
+      if (src16 != nullptr) h = __ldg(reinterpret_cast<const uint2*>(src16 + row * c + q));
+      else h = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      *reinterpret_cast<uint2*>(dst16 + row * ld + col0 + q) = h;
     }
   }
 }
@@ -256,9 +276,11 @@ int ft3d_col_sum(const float* x, int64_t n, int32_t channels, float* out, int32_
 }
 
 int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma, const float* beta,
-                  const float* res, int32_t relu, float* z, void* z16, const int32_t* valid_rows,
+                  const float* res, int32_t relu, float* z, void* z16, int64_t ldz, const int32_t* valid_rows,
                   ft3d_stream_t stream) {
   if (n == 0) return FT3D_OK;
+  if (ldz == 0) ldz = channels;
+  FT3D_REQUIRE(ldz >= channels && ldz % 4 == 0, "ft3d_bn_apply: output pitch must be a multiple of 4 and >= channels");
   FT3D_REQUIRE(y && stat && gamma && beta && (z || z16) && channels >= 4 && channels % 4 == 0,
                "ft3d_bn_apply: bad arguments");
   FT3D_REQUIRE(aligned16(y) && aligned16(stat) && aligned16(gamma) && aligned16(beta) && aligned16(res) &&
@@ -268,19 +290,33 @@ int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat
   ColGrid ga = col_grid(n, channels / 4);
   switch (row_batch()) {
     case 1: launch_pdl(bn_apply_kernel<1>, dim3(ga.grid), ga.block, 0, (cudaStream_t)stream, y, n, channels, ga.rows_per_cta, stat,
-             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows); break;
+             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, ldz, valid_rows); break;
     case 2: launch_pdl(bn_apply_kernel<2>, dim3(ga.grid), ga.block, 0, (cudaStream_t)stream, y, n, channels, ga.rows_per_cta, stat,
-             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows); break;
+             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, ldz, valid_rows); break;
     default: launch_pdl(bn_apply_kernel<4>, dim3(ga.grid), ga.block, 0, (cudaStream_t)stream, y, n, channels, ga.rows_per_cta, stat,
-             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, valid_rows); break;
+             gamma, beta, res, relu, z, (__nv_bfloat16*)z16, ldz, valid_rows); break;
   }
   return check_launch("ft3d_bn_apply");
 }
 
+int ft3d_copy_cols(const float* src, const void* src16, int64_t n, int32_t c, float* dst, void* dst16, int64_t ld,
+                   int32_t col0, ft3d_stream_t stream) {
+  if (n == 0) return FT3D_OK;
+  FT3D_REQUIRE(src && dst && c >= 4 && c % 4 == 0 && col0 % 4 == 0 && ld % 4 == 0 && ld >= col0 + c,
+               "ft3d_copy_cols: bad arguments");
+  FT3D_REQUIRE(aligned16(src) && aligned16(dst) && ((uintptr_t)src16 & 7) == 0 && ((uintptr_t)dst16 & 7) == 0,
+               "ft3d_copy_cols: pointers must be 16-byte aligned");
+  launch_pdl(copy_cols_kernel, dim3(grid_for(n * (c / 4), 256)), dim3(256), 0, (cudaStream_t)stream, src,
+             (const __nv_bfloat16*)src16, n, (int)c, dst, (__nv_bfloat16*)dst16, ld, (int)col0);
+  return check_launch("ft3d_copy_cols");
+}
+
 int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const float* z, int64_t n, int32_t channels,
-                       const float* stat, float* red, float* dgamma, float* dbeta, int32_t accumulate,
+                       const float* stat, float* red, float* dgamma, float* dbeta, int32_t accumulate, int64_t ldg,
                        const int32_t* valid_rows, void* workspace, size_t workspace_bytes, ft3d_stream_t stream) {
   FT3D_REQUIRE(n > 0, "ft3d_bn_bwd_reduce: needs at least one row");
+  if (ldg == 0) ldg = channels;
+  FT3D_REQUIRE(ldg >= channels && ldg % 4 == 0, "ft3d_bn_bwd_reduce: gz pitch must be a multiple of 4 and >= channels");
   FT3D_REQUIRE(gz && y && stat && red && dgamma && dbeta && workspace && channels >= 4 &&
                    channels % 4 == 0 && channels <= 1024,
                "ft3d_bn_bwd_reduce: bad arguments");
@@ -290,9 +326,9 @@ int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const f
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_bn_bwd_reduce: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
   switch (row_batch()) {
-    case 1: launch_pdl(bn_bwd_reduce_kernel<1>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows); break;
-    case 2: launch_pdl(bn_bwd_reduce_kernel<2>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows); break;
-    default: launch_pdl(bn_bwd_reduce_kernel<4>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, valid_rows); break;
+    case 1: launch_pdl(bn_bwd_reduce_kernel<1>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, ldg, valid_rows); break;
+    case 2: launch_pdl(bn_bwd_reduce_kernel<2>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, ldg, valid_rows); break;
+    default: launch_pdl(bn_bwd_reduce_kernel<4>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z, n, channels, g.rows_per_cta, stat, (float*)workspace, ldg, valid_rows); break;
   }
   launch_pdl(col_finalize_kernel<1>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream, (const float*)workspace, g.grid, channels, n, 0.f, 0.f, red, dgamma, dbeta, accumulate, valid_rows);
   return check_launch("ft3d_bn_bwd_reduce");
@@ -300,8 +336,10 @@ int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const f
 
 int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const float* z, int64_t n, int32_t channels,
                       const float* stat, const float* gamma, const float* red, float* gy, void* gy16, float* gres,
-                      const int32_t* valid_rows, ft3d_stream_t stream) {
+                      int64_t ldg, const int32_t* valid_rows, ft3d_stream_t stream) {
   if (n == 0) return FT3D_OK;
+  if (ldg == 0) ldg = channels;
+  FT3D_REQUIRE(ldg >= channels && ldg % 4 == 0, "ft3d_bn_bwd_apply: gz pitch must be a multiple of 4 and >= channels");
   FT3D_REQUIRE(gz && stat && gamma && (y || !red) && (gy || gy16 || gres) && channels >= 4 && channels % 4 == 0,
                "ft3d_bn_bwd_apply: bad arguments");
   FT3D_REQUIRE(aligned16(gz) && aligned16(y) && aligned16(z) && ((uintptr_t)z16 & 7) == 0 && aligned16(stat) &&
@@ -311,11 +349,11 @@ int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const fl
   ColGrid gb = col_grid(n, channels / 4);
   switch (row_batch()) {
     case 1: launch_pdl(bn_bwd_apply_kernel<1>, dim3(gb.grid), gb.block, 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z,
-             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows); break;
+             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, ldg, valid_rows); break;
     case 2: launch_pdl(bn_bwd_apply_kernel<2>, dim3(gb.grid), gb.block, 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z,
-             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows); break;
+             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, ldg, valid_rows); break;
     default: launch_pdl(bn_bwd_apply_kernel<4>, dim3(gb.grid), gb.block, 0, (cudaStream_t)stream, gz, y, (const __nv_bfloat16*)z16, z,
-             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, valid_rows); break;
+             n, channels, gb.rows_per_cta, stat, gamma, red, gy, (__nv_bfloat16*)gy16, gres, ldg, valid_rows); break;
   }
   return check_launch("ft3d_bn_bwd_apply");
 }

@@ -94,7 +94,7 @@ def _role(transpose: bool, grad: bool) -> str:
 
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, kernel, gamma, beta, res, x16, kmap, transpose, relu, bn):
+    def forward(ctx, feats, kernel, gamma, beta, res, x16, kmap, transpose, relu, bn, skip=None, skip16=None):
         ctx.set_materialize_grads(False)         # no zero-filled gradient for the (non-differentiable) bf16 output
         training = bn.training or bn.running_mean is None
         rm, rv = (bn.running_mean, bn.running_var) if (bn.training and bn.track_running_stats) else (None, None)
@@ -128,7 +128,13 @@ class _ConvBNAct(torch.autograd.Function):
                 stat = ops.bn_stats(y, bn.eps, bn.momentum, rm, rv)
             else:
                 stat = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)]).contiguous()
-        z, z16 = ops.bn_apply(y, stat, gamma, beta, res, relu, want_f32=True, want_bf16=tc)
+        # skip: torchsparse.cat([this block's output, skip]) (models/spvcnn.py:212-228) -- the normalise pass writes
+        # into the left columns of the concatenation buffers, one copy launch fills the right columns
+        extra = 0 if skip is None else skip.shape[1]
+        z, z16 = ops.bn_apply(y, stat, gamma, beta, res, relu, want_f32=True, want_bf16=tc, extra_cols=extra)
+        if extra:
+            ops.copy_cols(skip, skip16, z, z16, cout)
+        ctx.extra = extra
         ctx.kmap, ctx.transpose, ctx.relu, ctx.tc, ctx.training = kmap, transpose, relu, tc, training
         ctx.has_res = res is not None
         mask = (z16 if tc else z) if relu else None
@@ -142,7 +148,7 @@ class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gz, _unused):
         if gz is None:
-            return (None,) * 10
+            return (None,) * 12
         saved_in, kernel, gamma, y, stat, mask = ctx.saved_tensors
         beta = ctx.beta
         kmap, transpose, tc = ctx.kmap, ctx.transpose, ctx.tc
@@ -155,12 +161,14 @@ class _ConvBNAct(torch.autograd.Function):
             sink = None
         need_in, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         want_res = ctx.has_res and ctx.needs_input_grad[4] and mask is not None
+        ldg = gz.shape[1] if ctx.extra else 0          # gz and the saved output are [n, cout + extra]: row pitch
         if sink is not None:
-            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat, gamma.grad, beta.grad)
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat, gamma.grad, beta.grad, ldg=ldg)
         else:
-            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat)
+            red, dgamma, dbeta = ops.bn_bwd_reduce(gz, y, m16, m32, stat, ldg=ldg)
         gy, gy16, gres = ops.bn_bwd_apply(gz, y, m16, m32, stat, gamma, red if ctx.training else None,
-                                          want_f32=not tc, want_bf16=tc, want_res=want_res)
+                                          want_f32=not tc, want_bf16=tc, want_res=want_res, ldg=ldg)
+        gskip = gz[:, kernel.shape[-1]:] if (ctx.extra and ctx.needs_input_grad[10]) else None
         if ctx.has_res and ctx.needs_input_grad[4] and mask is None:
             gres = gz
         gin = gw = None
@@ -208,7 +216,7 @@ class _ConvBNAct(torch.autograd.Function):
         if sink is not None:
             sink.note(gamma)
             sink.note(beta)
-        return gin, gw, dgamma, dbeta, gres, None, None, None, None, None
+        return gin, gw, dgamma, dbeta, gres, None, None, None, None, None, gskip, None
 
 
 def _bn_forward(y, bn, training, rm, rv, gamma, beta, relu):
@@ -351,8 +359,10 @@ def _fusable(conv, bn) -> bool:
             and bn.momentum is not None and conv.out_channels % 4 == 0 and conv.d == 1)
 
 
-def conv_bn_act(x: SparseTensor, conv, bn, relu: bool, res: torch.Tensor | None = None) -> SparseTensor:
-    """``relu?(bn(conv(x)) [+ res])`` as one autograd node; ``res`` is an fp32 [N_out, Cout] tensor."""
+def conv_bn_act(x: SparseTensor, conv, bn, relu: bool, res: torch.Tensor | None = None,
+                skip: SparseTensor | None = None) -> SparseTensor:
+    """``relu?(bn(conv(x)) [+ res])`` as one autograd node; ``res`` is an fp32 [N_out, Cout] tensor.  With ``skip`` the
+    result is ``torchsparse.cat([that, skip])``: [N_out, Cout + skip channels]."""
     kmap, make_out = conv_geometry(x, conv.ks, conv.s, conv.d, conv.t)
     feats = x.F
     if not feats.is_contiguous():
@@ -360,7 +370,14 @@ def conv_bn_act(x: SparseTensor, conv, bn, relu: bool, res: torch.Tensor | None 
     x16 = x.F16
     if x16 is not None and (x16.shape != feats.shape or x16.dtype != torch.bfloat16):
         x16 = None
-    z, z16 = _ConvBNAct.apply(feats, conv.kernel, bn.weight, bn.bias, res, x16, kmap, conv.t, relu, bn)
+    if skip is None:
+        z, z16 = _ConvBNAct.apply(feats, conv.kernel, bn.weight, bn.bias, res, x16, kmap, conv.t, relu, bn)
+    else:
+        s16 = skip.F16
+        if s16 is not None and (s16.shape != skip.F.shape or s16.dtype != torch.bfloat16):
+            s16 = None
+        z, z16 = _ConvBNAct.apply(feats, conv.kernel, bn.weight, bn.bias, res, x16, kmap, conv.t, relu, bn,
+                                  skip.F.contiguous(), s16)
     if bn.training and bn.track_running_stats:
         bn._ft3d_pending_batches = getattr(bn, "_ft3d_pending_batches", 0) + 1
     out = make_out(z)
@@ -433,6 +450,19 @@ def _residual_forward(self, x):
     h = conv_bn_act(x, nm[0], nm[1], True)
     shortcut = x.F if not dm else conv_bn_act(x, dm[0], dm[1], False).F
     return conv_bn_act(h, nm[3], nm[4], True, res=shortcut.contiguous())
+
+
+def deconv_cat(block, y: SparseTensor, skip: SparseTensor) -> SparseTensor:
+    """``torchsparse.cat([block(y), skip])`` for a Basic(De)ConvolutionBlock (models/spvcnn.py:212,216,224,228): when the
+    block is fused, its BatchNorm epilogue writes straight into the concatenation buffer."""
+    net = getattr(block, "net", None)
+    mods = list(net) if isinstance(net, nn.Sequential) else []
+    if (len(mods) == 3 and _fusable(mods[0], mods[1]) and type(mods[2]) is spnn.ReLU and y.F.is_cuda
+            and getattr(net, "_ft3d_fused", False) and skip.F.shape[1] % 4 == 0
+            and skip.F.dtype == torch.float32 and y.F.dtype == torch.float32):
+        return conv_bn_act(y, mods[0], mods[1], True, skip=skip)
+    from . import cat
+    return cat([block(y), skip])
 
 
 def weight_packer(model: nn.Module):

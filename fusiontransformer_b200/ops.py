@@ -594,41 +594,50 @@ def col_sum(x, into=None):
     return out
 
 
-def bn_apply(y, stat, gamma, beta, res, relu: bool, want_f32: bool = True, want_bf16: bool = True):
+def bn_apply(y, stat, gamma, beta, res, relu: bool, want_f32: bool = True, want_bf16: bool = True, extra_cols: int = 0):
+    """``extra_cols`` > 0: the outputs are allocated [n, c + extra_cols] and written into their left c columns (row
+    pitch c + extra_cols): the caller fills the rest (``copy_cols``) -- a concatenation without a concatenation pass."""
     n, c = y.shape
-    z = torch.empty((n, c), dtype=torch.float32, device=y.device) if want_f32 else None
-    z16 = torch.empty((n, c), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    ld = c + extra_cols
+    z = torch.empty((n, ld), dtype=torch.float32, device=y.device) if want_f32 else None
+    z16 = torch.empty((n, ld), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
     lib().bn_apply(y.data_ptr(), n, c, stat.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(res), int(relu), _p(z),
-                   _p(z16), _valid(n), _stream())
+                   _p(z16), ld, _valid(n), _stream())
     return z, z16
 
 
-def bn_bwd_reduce(gz, y, z16, z, stat, dgamma_into=None, dbeta_into=None):
+def copy_cols(src, src16, dst, dst16, col0: int):
+    """dst[:, col0:col0+c] = src (and dst16[...] = src16, or bf16(src) when src16 is None) in one launch."""
+    n, c = src.shape
+    lib().copy_cols(src.data_ptr(), _p(src16), n, c, dst.data_ptr(), _p(dst16), dst.shape[1], int(col0), _stream())
+
+
+def bn_bwd_reduce(gz, y, z16, z, stat, dgamma_into=None, dbeta_into=None, ldg: int = 0):
     """-> (red [2,C], dgamma [C], dbeta [C]); with ``*_into`` the sums are ADDED to those tensors (gradient arena)
-    and (red, None, None) is returned."""
+    and (red, None, None) is returned.  ``ldg``: row pitch of gz and of the saved output (0 = C)."""
     n, c = y.shape
     dev = y.device
     red = torch.empty((2, c), dtype=torch.float32, device=dev)
     ws = bn_scratch(dev)
     if dgamma_into is not None:
         lib().bn_bwd_reduce(gz.data_ptr(), y.data_ptr(), _p(z16), _p(z), n, c, stat.data_ptr(), red.data_ptr(),
-                            dgamma_into.data_ptr(), dbeta_into.data_ptr(), 1, _valid(n), ws.data_ptr(), ws.numel(),
+                            dgamma_into.data_ptr(), dbeta_into.data_ptr(), 1, ldg, _valid(n), ws.data_ptr(), ws.numel(),
                             _stream())
         return red, None, None
     dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
     lib().bn_bwd_reduce(gz.data_ptr(), y.data_ptr(), _p(z16), _p(z), n, c, stat.data_ptr(), red.data_ptr(),
-                        dgb[0].data_ptr(), dgb[1].data_ptr(), 0, _valid(n), ws.data_ptr(), ws.numel(), _stream())
+                        dgb[0].data_ptr(), dgb[1].data_ptr(), 0, ldg, _valid(n), ws.data_ptr(), ws.numel(), _stream())
     return red, dgb[0], dgb[1]
 
 
-def bn_bwd_apply(gz, y, z16, z, stat, gamma, red, want_f32: bool, want_bf16: bool, want_res: bool):
-    n, c = gz.shape
+def bn_bwd_apply(gz, y, z16, z, stat, gamma, red, want_f32: bool, want_bf16: bool, want_res: bool, ldg: int = 0):
+    n, c = gz.shape[0], stat.shape[1]
     dev = gz.device
     gy = torch.empty((n, c), dtype=torch.float32, device=dev) if want_f32 else None
     gy16 = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if want_bf16 else None
     gres = torch.empty((n, c), dtype=torch.float32, device=dev) if want_res else None
     lib().bn_bwd_apply(gz.data_ptr(), _p(y), _p(z16), _p(z), n, c, stat.data_ptr(), gamma.data_ptr(), _p(red), _p(gy),
-                       _p(gy16), _p(gres), _valid(n), _stream())
+                       _p(gy16), _p(gres), ldg, _valid(n), _stream())
     return gy, gy16, gres
 
 

@@ -13,7 +13,8 @@ import os
 import torch
 from torch import nn
 
-from . import cat
+from . import cat  # noqa: F401  (re-exported: the reference calls torchsparse.cat)
+from .fused import deconv_cat
 from . import nn as spnn
 from .point_tensor import PointTensor
 from .sparse_tensor import SparseTensor
@@ -125,15 +126,15 @@ class SPVCNN(nn.Module):
 
         y1 = point_to_voxel(x4, z1)
         y1.F = self.dropout(y1.F)
-        y1 = self.up1[1](cat([self.up1[0](y1), x3]))
-        y2 = self.up2[1](cat([self.up2[0](y1), x2]))
+        y1 = self.up1[1](deconv_cat(self.up1[0], y1, x3))      # cat([deconv(y), skip]) written in place (fused.py)
+        y2 = self.up2[1](deconv_cat(self.up2[0], y1, x2))
         z2 = voxel_to_point(y2, z1)
         z2.F = z2.F + self.point_transforms[1](z1.F)
 
         y3 = point_to_voxel(y2, z2)
         y3.F = self.dropout(y3.F)
-        y3 = self.up3[1](cat([self.up3[0](y3), x1]))
-        y4 = self.up4[1](cat([self.up4[0](y3), x0]))
+        y3 = self.up3[1](deconv_cat(self.up3[0], y3, x1))
+        y4 = self.up4[1](deconv_cat(self.up4[0], y3, x0))
         z3 = voxel_to_point(y4, z2)
         z3.F = z3.F + self.point_transforms[2](z2.F)
         if taps is not None:

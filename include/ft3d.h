@@ -278,20 +278,26 @@ int ft3d_col_sum(const float* x, int64_t n, int32_t channels, float* out, int32_
 /* z = [relu]((y - mean) * rstd * gamma + beta [+ res]); writes z f32 [n,C] (nullable) and z16 bf16 [n,C]
  * (nullable) -- the copy the next convolution gathers.  Evaluation mode: pass stat built from the running stats. */
 int ft3d_bn_apply(const float* y, int64_t n, int32_t channels, const float* stat, const float* gamma,
-                  const float* beta, const float* res, int32_t relu, float* z, void* z16,
+                  const float* beta, const float* res, int32_t relu, float* z, void* z16, int64_t ldz,
                   const int32_t* valid_rows, ft3d_stream_t stream);
+/* torchsparse.cat([deconv(y), skip]) (models/spvcnn.py:212,216,224,228) without a concatenation pass: ft3d_bn_apply
+ * writes z / z16 with row pitch ldz (0 = channels) straight into the left columns of the [n, C1+C2] buffers, and
+ * ft3d_copy_cols puts the skip tensor (fp32 and its bf16 copy; src16 NULL: rounded here) at column col0 of the same
+ * buffers.  The backward kernels read gz and the saved output with the same pitch (ldg). */
+int ft3d_copy_cols(const float* src, const void* src16, int64_t n, int32_t c, float* dst, void* dst16, int64_t ld,
+                   int32_t col0, ft3d_stream_t stream);
 /* g' = gz * [z > 0] (mask from z16 if given, else z, else none).  red f32 [2,C] = (sum g'/n, sum g' xhat/n);
  * dgamma = sum g' xhat; dbeta = sum g' (accumulate != 0: added to the values already there, so the gradients can
  * be written straight into a flat gradient arena). */
 int ft3d_bn_bwd_reduce(const float* gz, const float* y, const void* z16, const float* z, int64_t n,
                        int32_t channels, const float* stat, float* red, float* dgamma, float* dbeta,
-                       int32_t accumulate, const int32_t* valid_rows, void* workspace, size_t workspace_bytes,
-                       ft3d_stream_t stream);
+                       int32_t accumulate, int64_t ldg, const int32_t* valid_rows, void* workspace,
+                       size_t workspace_bytes, ft3d_stream_t stream);
 /* gy = gamma rstd (g' - c1 - xhat c2)  (red == NULL: frozen statistics, gy = gamma rstd g'); outputs (each
  * nullable): gy f32, gy16 bf16 (the dgrad / wgrad operand), gres f32 = g' (gradient of the residual input). */
 int ft3d_bn_bwd_apply(const float* gz, const float* y, const void* z16, const float* z, int64_t n,
                       int32_t channels, const float* stat, const float* gamma, const float* red, float* gy,
-                      void* gy16, float* gres, const int32_t* valid_rows, ft3d_stream_t stream);
+                      void* gy16, float* gres, int64_t ldg, const int32_t* valid_rows, ft3d_stream_t stream);
 
 /* ---- segmentation loss and metric on the device ----------------------------------------------
  * ft3d_seg_loss: modules/SemanticTorchpackTrainer.py:70-108.  loss = (1-l) * CE + l * KL with

@@ -90,7 +90,9 @@ def test_error_convention_of_the_hot_path_entry_points():
         L.seg_loss(p, p, 100, 20, -100, None, None, 0.5, None, p, p, p, 1 << 20, None)
     # zero-size work is a no-op that succeeds without touching the device
     L.conv_pairs_tc(p, p, p, 27, 0, 0, 64, 64, p, p, None)
-    L.bn_apply(p, 0, 64, p, p, p, None, 1, p, None, None, None)
+    L.bn_apply(p, 0, 64, p, p, p, None, 1, p, None, 0, None, None)
+    with pytest.raises(_lib.Ft3dError, match="output pitch"):
+        L.bn_apply(p, 10, 64, p, p, p, None, 1, p, None, 32, None, None)            # pitch smaller than the row
     L.confusion_update(p, p, 0, 20, -100, None, p, None)
     assert int(L.seg_loss_workspace()) >= 3 * 1024 * 8 and int(L.bn_workspace(256)) > 0
 

@@ -299,3 +299,44 @@ def test_fused_point_mlp_matches_torch(monkeypatch, mode, tol, inc, outc, sink):
         err = (pg.grad.double().cpu() - po.grad).norm().item() / scale
         assert err < gtol, (name, err)
     assert rel_l2(mlp[1].running_var, ref[1].running_var) < 1e-4
+
+
+@pytest.mark.parametrize("mode,tol", [("f32", 1e-4), ("tc", 5e-3)])
+def test_deconv_cat_in_place_equals_cat(monkeypatch, small_batch, mode, tol):
+    """torchsparse.cat([deconv(y), skip]) (models/spvcnn.py:212-228) with the BatchNorm epilogue writing straight into
+    the concatenation buffer: same forward as block + torch.cat, same gradients for y, the skip and the parameters."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import spvcnn as sp
+    from fusiontransformer_b200.fused import deconv_cat, fuse
+    monkeypatch.setenv("FT3D_CONV", mode)
+    spf = ft.nn.functional
+    torch.manual_seed(2)
+    C = small_batch["coords"].int().cuda()
+    x = ft.SparseTensor(torch.randn(C.shape[0], 32, device="cuda"), C, 1)
+    x.check()
+    down = sp.BasicConvolutionBlock(32, 64, ks=2, stride=2).cuda().train()
+    up_a = sp.BasicDeconvolutionBlock(64, 96, ks=2, stride=2).cuda().train()
+    up_b = sp.BasicDeconvolutionBlock(64, 96, ks=2, stride=2).cuda().train()
+    up_b.load_state_dict(up_a.state_dict())
+    fuse(down), fuse(up_a), fuse(up_b)
+    outs = []
+    for up, inplace in ((up_a, True), (up_b, False)):
+        xf = x.F.clone().requires_grad_(True)
+        xin = ft.SparseTensor(xf, C, 1)
+        xin.check()
+        skip_f = torch.randn(C.shape[0], 32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)).requires_grad_(True)
+        skip = ft.SparseTensor(skip_f, C, 1)
+        y = down(xin)
+        out = deconv_cat(up, y, skip) if inplace else ft.cat([up(y), skip])
+        assert out.F.shape == (C.shape[0], 96 + 32)
+        w = torch.randn(out.F.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
+        (out.F * w).sum().backward()
+        outs.append((out.F.detach(), None if out.F16 is None else out.F16.float(), xf.grad, skip_f.grad,
+                     up.net[0].kernel.grad.clone(), up.net[1].weight.grad.clone()))
+        for p in list(down.parameters()):
+            p.grad = None
+    a, b = outs
+    assert rel_l2(a[0], b[0]) < 1e-6 and rel_l2(a[3], b[3]) < 1e-6            # same kernels, same rows
+    if a[1] is not None:                                                      # bf16 twin of the whole concatenation
+        assert a[1].shape == a[0].shape and rel_l2(a[1], b[0].bfloat16().float()) < 1e-6
+    assert rel_l2(a[2], b[2]) < 1e-4 and rel_l2(a[4], b[4]) < 1e-4 and rel_l2(a[5], b[5]) < 1e-4
