@@ -28,7 +28,8 @@ static inline ColGrid col_grid(int64_t n_rows, int cv) {
   if (ry > 32) ry = 32;
   g.block = dim3((unsigned)cv, (unsigned)ry, 1);
   int64_t want = (n_rows + ry - 1) / ry;                 // CTAs if each did one row per lane
-  int64_t ctas = want < kColMaxCtas ? want : kColMaxCtas;
+  const int64_t cap = col_cta_cap();
+  int64_t ctas = want < cap ? want : cap;
   if (ctas < 1) ctas = 1;
   int64_t rpc = (n_rows + ctas - 1) / ctas;
   rpc = (rpc + ry - 1) / ry * ry;

@@ -66,6 +66,7 @@ __device__ __forceinline__ void pdl_enter() {
 }
 
 int row_batch();    // FT3D_ROWBATCH = 1 | 2 | 4: rows a thread of the streaming kernels keeps in flight (default 2, measured best on B200)
+int col_cta_cap();  // FT3D_COL_CTAS: upper bound on the CTAs of a column-reduction / BatchNorm streaming launch (<= 8 per SM)
 bool pdl_enabled();   // FT3D_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops)
 
 template <typename... KArgs, typename... Args>

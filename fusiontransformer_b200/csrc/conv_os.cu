@@ -34,11 +34,13 @@ constexpr int kOsThreads = 320;
 constexpr int kOsMaxSlots = 10;
 constexpr int kOsStageFloats = 32 * 36;        // one epilogue warp: 32 rows x (32 + 4 pad) floats
 constexpr int kOsProducers = 128;              // warps 0-3
+constexpr int kOsAhead = 4;                    // passes whose indices are in flight in a TMA producer warp
 
 struct OsHeader {
   uint64_t full[kOsMaxSlots];
   uint64_t empty[kOsMaxSlots];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t pfull[kOsMaxSlots];                 // CTA pairs: rank 1's half of the stage has landed (remote arrive)
   uint32_t tmem_base;
   int32_t idx[2][kTileRows];                   // LDGSTS mode: gather indices of the pass being issued
 };
@@ -59,6 +61,8 @@ struct OsArgs {
   int64_t n_out;
   int unit_cap, K, kflip, red, ncols, nslots, tcols, nbuf;
   int cs, tile_rows;          // CTAs per cluster (1, 2, 4) and rows of a schedule tile (128 * cs)
+  int dbg;                    // FT3D_OS_DEBUG, timing experiments only (results are then meaningless): 1 = no MMAs,
+                              // 2 = no A gathers, 4 = no B copies (tools/conv_os_probe.py --ablate)
 };
 
 __device__ __forceinline__ void os_cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
@@ -69,6 +73,18 @@ __device__ __forceinline__ void os_cp_async_arrive_noinc(uint64_t* bar) {
 }
 __device__ __forceinline__ void os_named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// true in exactly one lane of the (fully active) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ unsigned long long os_now() {
   unsigned long long t;
@@ -117,6 +133,61 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): the two CTAs of a cluster issue ONE tcgen05.mma of M = 256 per k-step.  Each CTA keeps
+// its own 128 gathered A rows and only HALF of the weight block (N/2 columns) in shared memory; the tensor cores of the
+// pair read both halves, so a weight block enters each SM once per 256 output rows instead of once per 128 -- the
+// multicast above saves L2 reads but not SM ingress, which is what bounds the wide layers.  Rank 0 issues the MMAs and
+// commits to both CTAs' barriers; rank 1's MMA warp only relays "my half of stage s has landed" to rank 0.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {   // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {     // pairs with a remote arrive
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITC_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAITC_DONE;\n"
+      "bra WAITC_LOOP;\n"
+      "WAITC_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // walks the passes of this CTA's work units u = first, first + step, ... (units without passes are skipped); the
 // record of the following unit is requested one unit ahead so that crossing a unit boundary costs no L2 round trip
 struct OsPassIter {
@@ -152,15 +223,17 @@ struct OsPassIter {
   }
 };
 
-template <bool TMA>
+template <bool TMA, bool PAIR>
 __global__ void __launch_bounds__(kOsThreads)
 conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
+  static_assert(TMA || !PAIR, "CTA pairs use the TMA gather");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int red = a.red, ncols = a.ncols, nslots = a.nslots;
   const int nkb = (red + 63) / 64;
   const int b_bytes = ncols * kBlockRowBytes;
-  const int stage_bytes = kBlockBytes + b_bytes;
+  const int b_stage = PAIR ? b_bytes / 2 : b_bytes;                        // a CTA of a pair holds half the columns
+  const int stage_bytes = kBlockBytes + b_stage;
   float* staging = reinterpret_cast<float*>(smem + (size_t)nslots * stage_bytes);
   float* sstat = staging + 4 * kOsStageFloats;                                   // [4 warps][2][ncols]
   OsHeader* hdr = reinterpret_cast<OsHeader*>(sstat + 4 * 2 * ncols);
@@ -174,15 +247,22 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
       mbar_init(&hdr->full[s], TMA ? 1 : kOsProducers + 1);
-      mbar_init(&hdr->empty[s], (uint32_t)cs);                             // every CTA of the cluster has consumed it
+      mbar_init(&hdr->empty[s], PAIR ? 1u : (uint32_t)cs);                 // every MMA issuer of the cluster has consumed it
+      mbar_init(&hdr->pfull[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&hdr->acc_full[b], 1);
-      mbar_init(&hdr->acc_empty[b], 128);
+      mbar_init(&hdr->acc_empty[b], PAIR ? 256 : 128);                     // pair: both CTAs' epilogues free rank 0's MMA
     }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)(a.nbuf * a.tcols));
+  if (PAIR) {
+    __syncthreads();
+    cluster_sync_all();             // both CTAs are resident and their barriers initialised before the paired allocation
+    if (warp == 0) tmem_alloc_pair(&hdr->tmem_base, (uint32_t)(a.nbuf * a.tcols));
+  } else if (warp == 0) {
+    tmem_alloc(&hdr->tmem_base, (uint32_t)(a.nbuf * a.tcols));
+  }
   tc_fence_before();
   __syncthreads();
   if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
@@ -193,48 +273,90 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   if (U > a.unit_cap) U = a.unit_cap;
   unsigned long long* tr = a.trace != nullptr ? a.trace + (size_t)blockIdx.x * 8 : nullptr;
   if (tr != nullptr && tid == 0) tr[0] = os_now();
+  // per-stage stamps of CTA 0 behind the per-CTA records: [stage][4] = {issued, landed, MMAs committed, -} for the first
+  // 512 stages, then [unit][2] = {accumulator ready, rows written} from offset 2048 (tools/conv_os_probe.py --fine)
+  unsigned long long* fine = (a.trace != nullptr && blockIdx.x == 0) ? a.trace + (size_t)kNumSMs * 8 : nullptr;
 
   if (TMA && warp < 4) {
     // ------------------------------------------------------------------ producers: TMA gather4 (A) + bulk copy (B)
     // A 128 x 64 block is 32 gather4 loads; a warp issues them lane by lane (the operands of a TMA instruction are
     // warp-uniform), so the four producer warps each take a quarter of the block: lanes 0-7 of warp w load rows
     // w*32 + 4*lane .. +3.  Warp 0 also arms the stage's mbarrier with the byte count and adds the B block.
+    // The offset and the gather indices of a pass are requested kOsAhead passes before they are needed: a narrow layer
+    // issues a pass in ~0.2 us, far less than a loaded L2 round trip, so a one-pass look-ahead left the producers
+    // waiting for indices (0.6-0.7 us per pass measured on the 32- and 64-channel layers).
     OsPassIter it;
     it.init(a.units, U, first, step);
-    int k_n = 0;
-    int4 r_n = make_int4(-1, -1, -1, -1);
     const int sub = lane & 7;
-    if (it.valid()) {
-      k_n = __ldg(a.pass_k + it.pass());
-      r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
+    int kq[kOsAhead];
+    int4 rq[kOsAhead];
+    int queued = 0;
+#pragma unroll
+    for (int d = 0; d < kOsAhead; ++d) {
+      kq[d] = 0;
+      rq[d] = make_int4(-1, -1, -1, -1);
+      if (it.valid()) {
+        kq[d] = __ldg(a.pass_k + it.pass());
+        rq[d] = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
+        it.next();
+        ++queued;
+      }
     }
     uint32_t cnt = 0, npass = 0;
-    while (it.valid()) {
-      const int k = a.kflip ? a.K - 1 - k_n : k_n;
-      const int4 r4 = r_n;
-      it.next();
+    while (queued > 0) {
+#pragma unroll
+     for (int d = 0; d < kOsAhead; ++d) {
+      if (queued == 0) break;
+      const int k = a.kflip ? a.K - 1 - kq[d] : kq[d];
+      const int4 r4 = rq[d];
+      --queued;
       ++npass;
-      if (it.valid()) {                                    // next pass's indices travel under this pass's issue
-        k_n = __ldg(a.pass_k + it.pass());
-        r_n = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
+      if (it.valid()) {                                    // refill the slot just consumed: pass + kOsAhead
+        kq[d] = __ldg(a.pass_k + it.pass());
+        rq[d] = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
+        it.next();
+        ++queued;
+      }
+      // the eight gather4 of this warp take their row indices from lanes 0-7; every lane walks the loop (uniform
+      // control flow: the TMA operands are built in uniform registers) and one elected lane issues
+      int rr[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rr[i][0] = __shfl_sync(0xffffffffu, r4.x, i); rr[i][1] = __shfl_sync(0xffffffffu, r4.y, i);
+        rr[i][2] = __shfl_sync(0xffffffffu, r4.z, i); rr[i][3] = __shfl_sync(0xffffffffu, r4.w, i);
       }
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         const int slot = (int)(cnt % (uint32_t)nslots);
         const uint32_t use = cnt / (uint32_t)nslots;
         if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
         uint8_t* st = smem + (size_t)slot * stage_bytes;
-        if (warp == 0 && lane == 0) {
-          mbar_arrive_expect_tx(&hdr->full[slot], (uint32_t)(kBlockBytes + b_bytes));
-          const uint8_t* bsrc = a.wpacked + ((size_t)k * nkb + kb) * b_bytes;
-          if (cs == 1)
-            bulk_g2s(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot]);
-          else if (rank == 0)     // one L2 read for the whole cluster; every CTA's full[slot] gets its complete_tx
-            bulk_g2s_multicast(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot], cmask);
+        if (fine != nullptr && tid == 0 && cnt < 512) fine[cnt * 4] = os_now();
+        if (elect_one()) {
+          if (warp == 0) {
+            mbar_arrive_expect_tx(&hdr->full[slot], (uint32_t)(((a.dbg & 2) ? 0 : kBlockBytes) + ((a.dbg & 4) ? 0 : b_stage)));
+            const uint8_t* bsrc = a.wpacked + ((size_t)k * nkb + kb) * b_bytes;
+            if (a.dbg & 4) {
+            } else if (PAIR) {        // columns [c*ncw + rank*ncw/2, +ncw/2) of each MMA's N range: this CTA's half
+              const int nsp = ncols > 256 ? 2 : 1;
+              const int half = (ncols / nsp / 2) * kBlockRowBytes;
+              for (int c = 0; c < nsp; ++c)
+                bulk_g2s(st + kBlockBytes + c * half, bsrc + (size_t)(2 * c + rank) * half, (uint32_t)half, &hdr->full[slot]);
+            } else if (cs == 1) {
+              bulk_g2s(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot]);
+            } else if (rank == 0) {   // one L2 read for the whole cluster; every CTA's full[slot] gets its complete_tx
+              bulk_g2s_multicast(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot], cmask);
+            }
+          }
+          if (!(a.dbg & 2)) {
+            const uint32_t dst = smem_u32(st) + (uint32_t)(warp * 8) * 512u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              tma_gather4(dst + (uint32_t)i * 512u, &tmap, kb * 64, rr[i][0], rr[i][1], rr[i][2], rr[i][3], &hdr->full[slot]);
+          }
         }
-        if (lane < 8)
-          tma_gather4(smem_u32(st) + (uint32_t)(warp * 8 + lane) * 512u, &tmap, kb * 64, r4.x, r4.y, r4.z, r4.w,
-                      &hdr->full[slot]);
+        __syncwarp();
       }
+     }
     }
     if (tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = npass;
   } else if (!TMA && warp < 4) {
@@ -289,10 +411,33 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (PAIR && rank != 0) {
+      // rank 1 of a pair: tell rank 0's MMA issuer when this CTA's half of a stage has landed
+      if (lane == 0) {
+        uint32_t cnt = 0;
+        int np_n = first < U ? __ldg(a.units + 2 * (int64_t)first).y : 0;
+        for (int u = first; u < U; u += step) {
+          const int np = np_n;
+          if (u + step < U) np_n = __ldg(a.units + 2 * (int64_t)(u + step)).y;
+          for (int q = 0; q < np * nkb; ++q, ++cnt) {
+            const int slot = (int)(cnt % (uint32_t)nslots);
+            mbar_wait(&hdr->full[slot], (cnt / (uint32_t)nslots) & 1);
+            mbar_arrive_remote(&hdr->pfull[slot], 0);
+          }
+        }
+      }
+    } else {
+      // All 32 lanes walk the schedule together and ONE elected lane issues: with uniform control flow the shared-
+      // memory descriptors, TMEM addresses and barrier addresses live in uniform registers, so an MMA costs a handful
+      // of instructions.  (Issued from inside an `if (lane == 0)` region the compiler wraps every tcgen05 instruction
+      // in an elect/broadcast loop: ~30 dependent instructions per MMA, measured 165 ns per MMA whatever its N.)
       const int nsplit = ncols > 256 ? 2 : 1;
       const int ncw = ncols / nsplit;
-      const uint32_t idesc = umma_idesc_bf16(128, ncw, 0, 0);
+      const int b_rows = PAIR ? ncw / 2 : ncw;             // rows of one MMA's B operand held by this CTA
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ncw, 0, 0);
+      const uint64_t dhi = smem_desc_sw128(0, 16, 1024);   // descriptor without its start address
+      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t c_step = (uint32_t)(b_rows * kBlockRowBytes) >> 4;
       uint32_t cnt = 0, use_acc = 0;
       int np_n = first < U ? __ldg(a.units + 2 * (int64_t)first).y : 0;
       for (int u = first; u < U; u += step) {
@@ -301,7 +446,10 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         if (np == 0) continue;
         const int buf = (int)(use_acc % (uint32_t)a.nbuf);
         const uint32_t ub = use_acc / (uint32_t)a.nbuf;
-        if (ub > 0) mbar_wait(&hdr->acc_empty[buf], (ub & 1) ^ 1);     // the epilogue has drained this accumulator
+        if (ub > 0) {                                                  // the epilogue has drained this accumulator
+          if (PAIR) mbar_wait_cluster(&hdr->acc_empty[buf], (ub & 1) ^ 1);
+          else mbar_wait(&hdr->acc_empty[buf], (ub & 1) ^ 1);
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * a.tcols);
         for (int q = 0; q < np; ++q) {
@@ -309,26 +457,43 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
             const int slot = (int)(cnt % (uint32_t)nslots);
             const uint32_t use = cnt / (uint32_t)nslots;
             mbar_wait(&hdr->full[slot], use & 1);
+            if (PAIR) mbar_wait_cluster(&hdr->pfull[slot], use & 1);
             if (!TMA) fence_proxy_async_smem();            // cp.async (generic proxy) data -> tensor-core reads
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + (size_t)slot * stage_bytes);
-            const uint32_t b_addr = a_addr + kBlockBytes;
-            const int ksteps = (red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4;
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t da = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
-              for (int c = 0; c < nsplit; ++c)
-                umma_bf16(tmem_d + (uint32_t)(c * ncw), da,
-                          smem_desc_sw128(b_addr + c * ncw * kBlockRowBytes + kk * 32, 16, 1024), idesc,
-                          (q | kb | kk) != 0);
+            if (fine != nullptr && lane == 0 && cnt < 512) fine[cnt * 4 + 1] = os_now();
+            const uint32_t a_addr = smem0 + (uint32_t)slot * (uint32_t)stage_bytes;
+            const uint64_t da0 = dhi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+            const uint64_t db0 = dhi | (uint64_t)(((a_addr + kBlockBytes) >> 4) & 0x3FFF);
+            const int ksteps = (a.dbg & 1) ? 0 : ((red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {             // one k-step = 16 bf16 = 32 bytes = 2 descriptor units
+                if (kk < ksteps) {
+                  const uint32_t acc = (uint32_t)((q | kb | kk) != 0);
+                  if (PAIR) umma_bf16_pair(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
+                  else umma_bf16(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
+                  if (nsplit == 2) {
+                    if (PAIR) umma_bf16_pair(tmem_d + (uint32_t)ncw, da0 + 2 * kk, db0 + c_step + 2 * kk, idesc, acc);
+                    else umma_bf16(tmem_d + (uint32_t)ncw, da0 + 2 * kk, db0 + c_step + 2 * kk, idesc, acc);
+                  }
+                }
+              }
+              if (PAIR) umma_commit_pair(&hdr->empty[slot], cmask);
+              else if (cs == 1) umma_commit(&hdr->empty[slot]);
+              else umma_commit_multicast(&hdr->empty[slot], cmask);
             }
-            if (cs == 1) umma_commit(&hdr->empty[slot]);
-            else umma_commit_multicast(&hdr->empty[slot], cmask);
+            __syncwarp();
+            if (fine != nullptr && lane == 0 && cnt < 512) fine[cnt * 4 + 2] = os_now();
           }
         }
-        umma_commit(&hdr->acc_full[buf]);
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(&hdr->acc_full[buf], cmask);
+          else umma_commit(&hdr->acc_full[buf]);
+        }
+        __syncwarp();
         ++use_acc;
       }
-      if (tr != nullptr) tr[2] = os_now();
+      if (tr != nullptr && lane == 0) tr[2] = os_now();
     }
   } else if (warp >= 6) {
     // ------------------------------------------------------------------ epilogue (TMEM quadrant = warp % 4)
@@ -355,6 +520,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
       const int4 u0 = u0_n, u1 = u1_n;                     // {first pass, passes, tile, chunks}, {chunk, scratch base}
       if (u + step < U) u0_n = __ldg(a.units + 2 * (int64_t)(u + step)), u1_n = __ldg(a.units + 2 * (int64_t)(u + step) + 1);
       const int tile = u0.z, chunks = u0.w;
+      if (tile < 0) continue;                              // hole of the unit placement (os_plan.cu)
       const int my_row = __ldg(a.out_row + (int64_t)tile * a.tile_rows + row_base + q * 32 + lane);
       if (u0.y == 0) {                                     // rows without any neighbour: the result is zero
         if (my_row >= 0)
@@ -365,6 +531,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
       const int buf = (int)(use_acc % (uint32_t)a.nbuf);
       mbar_wait(&hdr->acc_full[buf], (use_acc / (uint32_t)a.nbuf) & 1);
       tc_fence_after();
+      if (fine != nullptr && te == 0 && use_acc < 64) fine[2048 + use_acc * 2] = os_now();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * a.tcols) + ((uint32_t)(q * 32) << 16);
       // split tile: this unit's partial rows go to its scratch slot, [slot][tile row][ncols]
       float* part = chunks > 1 ? a.scratch + ((size_t)(u1.y + u1.x) * a.tile_rows + row_base + q * 32) * ncols : nullptr;
@@ -412,8 +579,10 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         }
         __syncwarp();
       }
+      if (fine != nullptr && te == 0 && use_acc < 64) fine[2048 + use_acc * 2 + 1] = os_now();
       tc_fence_before();
-      mbar_arrive(&hdr->acc_empty[buf]);
+      if (PAIR) mbar_arrive_remote(&hdr->acc_empty[buf], 0);
+      else mbar_arrive(&hdr->acc_empty[buf]);
       ++use_acc;
     }
     if (tr != nullptr && te == 0) tr[3] = os_now(), tr[6] = nunits | ((unsigned long long)nsplit_units << 32);
@@ -431,7 +600,10 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   tc_fence_before();
   __syncthreads();
   if (cs > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
-  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)(a.nbuf * a.tcols));
+  if (warp == 0) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)(a.nbuf * a.tcols));
+    else tmem_dealloc(tmem_base, (uint32_t)(a.nbuf * a.tcols));
+  }
 }
 
 // Fold of the split tiles: out[row] = sum of the tile's unit partials IN UNIT ORDER (ascending offsets), one CTA per
@@ -538,6 +710,11 @@ static int os_gather_mode() {      // 1 = TMA gather4 (default), 0 = LDGSTS; rea
   return (e != nullptr && (e[0] == 'l' || e[0] == 'L')) ? 0 : 1;
 }
 
+static bool os_pair_mode() {       // 256-row tiles: cta_group::2 pairs (default) or, FT3D_OS_PAIR=0, two CTAs + B multicast
+  const char* e = getenv("FT3D_OS_PAIR");
+  return e == nullptr || e[0] != '0';
+}
+
 constexpr int kOsMaxCtas = kNumSMs;
 
 constexpr int kOsFoldSlices = 4;                 // CTAs per split tile in the fold kernel
@@ -600,17 +777,23 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
   a.nbuf = 2 * a.tcols <= 512 ? 2 : 1;
   a.cs = tile_rows / tc::kTileRows;
   a.tile_rows = tile_rows;
-  const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes;
+  {
+    const char* e = getenv("FT3D_OS_DEBUG");
+    a.dbg = e ? atoi(e) : 0;
+  }
+  const bool tma = os_gather_mode() == 1;
+  const bool pair = tma && a.cs == 2 && os_pair_mode();      // 256-row tiles: one cta_group::2 MMA per CTA pair
+  const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes / (pair ? 2 : 1);
   const int fixed = 4 * kOsStageFloats * (int)sizeof(float) + 8 * ncols * (int)sizeof(float) + (int)sizeof(OsHeader) + 1024 + 64;
   int nslots = (227 * 1024 - fixed) / stage_bytes;
   if (nslots > kOsMaxSlots) nslots = kOsMaxSlots;
   FT3D_REQUIRE(nslots >= 2, "ft3d_conv_os: red=%d ncols=%d does not fit shared memory", red, ncols);
   a.nslots = nslots;
   const int smem_bytes = fixed + nslots * stage_bytes;
-  const int64_t max_clusters = kOsMaxCtas / a.cs;
-  const unsigned grid = (unsigned)((tiles < max_clusters ? tiles : max_clusters) * a.cs);
+  // every cluster runs: the unit array is laid out for kNumSMs / cs clusters (os_assign_kernel), and a map with fewer
+  // tiles than SMs still has enough units (split tiles) to occupy them
+  const unsigned grid = (unsigned)((kOsMaxCtas / a.cs) * a.cs);
   CUtensorMap tm;
-  const bool tma = os_gather_mode() == 1;
   FT3D_REQUIRE(tma || a.cs == 1, "ft3d_conv_os: cluster schedules (tile_rows > 128) need the TMA gather mode");
   if (tma) {
     int rc = make_row_tmap(&tm, in_bf16, n_in, red);
@@ -620,8 +803,9 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
   }
   static int configured = 0;
   if (!configured) {
-    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 1;
   }
   cudaStream_t s = (cudaStream_t)stream;
@@ -640,11 +824,12 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, conv_os_kernel<true>, tm, a);
+    if (pair) cudaLaunchKernelEx(&cfg, conv_os_kernel<true, true>, tm, a);
+    else cudaLaunchKernelEx(&cfg, conv_os_kernel<true, false>, tm, a);
   } else if (tma) {
-    launch_pdl(conv_os_kernel<true>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
+    launch_pdl(conv_os_kernel<true, false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
   } else {
-    launch_pdl(conv_os_kernel<false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
+    launch_pdl(conv_os_kernel<false, false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
   }
   int nparts = (int)grid;
   if (scratch_slots > 0) {                       // the schedule has split tiles: fold their unit partials

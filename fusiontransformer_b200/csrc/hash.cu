@@ -25,6 +25,13 @@ int row_batch() {
   return rb;
 }
 
+int col_cta_cap() {
+  const char* e = getenv("FT3D_COL_CTAS");       // read per call: tools/bn_probe.py sweeps it inside one process
+  int v = e ? atoi(e) : 0;
+  if (v < 1 || v > kNumSMs * 8) v = kNumSMs * 8;
+  return v;
+}
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {

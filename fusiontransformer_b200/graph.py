@@ -130,7 +130,11 @@ class StaticGeometry:
                     name = "%s.os_%s%d" % (key, side, trows)
                     n_pass, n_unit, n_slot = op.host_counts()[:3]
                     old = prev.pass_caps.get(name, (0, 0, 0)) if prev is not None else (0, 0, 0)
-                    pcap, ucap, scap = (max(int(n_pass * 1.25) + 8, old[0]), max(int(n_unit * 1.25) + 8, tcap, old[1]),
+                    # the unit array holds whole rounds of one unit per CTA cluster (os_plan.cu: placement), so its
+                    # length moves in steps of ncl: one spare round on top of the head-room
+                    ncl = 148 // (trows // 128)
+                    pcap, ucap, scap = (max(int(n_pass * 1.25) + 8, old[0]),
+                                        max((-(-int(n_unit * 1.25) // ncl) + 1) * ncl, tcap, old[1]),
                                         max(int(n_slot * 1.5) + 8, old[2]))
                     self.pass_caps[name] = (pcap, ucap, scap)
                     # `num` carries the batch's real unit count: the kernel never walks the padding units

@@ -474,7 +474,8 @@ def conv_os_plan(table: torch.Tensor, k: int, max_pairs: int | None = None, tile
     if max_pairs is not None:
         cap = max(min(cap, int(max_pairs)), 1)         # every pass holds at least one pair
     chunk = int(OS_CHUNK_PASSES)
-    ucap = 4 * T                                       # a tile is split into at most 4 units
+    ucap = 4 * T + 148                                 # a tile is split into at most 4 units; the placement of the
+                                                       # units over the CTA clusters pads the last round (os_plan.cu)
     units = torch.empty((ucap, 8), dtype=torch.int32, device=dev)
     split_tiles = torch.empty((max(T, 1), 4), dtype=torch.int32, device=dev)
     out_row = torch.empty(T * tile_rows, dtype=torch.int32, device=dev)
@@ -502,7 +503,8 @@ def os_scratch(device, nbytes: int):
     return hit
 
 
-OS_TRACE = None      # when a list: conv_os appends (tag, per-CTA trace tensor [grid,8] int64); tools/conv_os_probe.py
+OS_TRACE = None      # when a list: conv_os appends its trace tensor (int64: [148, 8] per-CTA records, then CTA 0's
+                     # per-stage stamps, csrc/conv_os.cu); tools/conv_os_probe.py
 
 
 def conv_os(x16, plan: OsPlan, w, w_transposed: bool, kflip: bool, n_out: int, owner=None, bn=None,
@@ -527,7 +529,7 @@ def conv_os(x16, plan: OsPlan, w, w_transposed: bool, kflip: bool, n_out: int, o
     ws = os_scratch(dev, lib().conv_os_workspace(ncols, slots, plan.tile_rows))
     trace = None
     if OS_TRACE is not None:
-        trace = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+        trace = torch.zeros((148 * 8 + 2048 + 128,), dtype=torch.int64, device=dev)
         OS_TRACE.append(trace)
     lib().conv_os(x16.data_ptr(), x16.shape[0], plan.units.data_ptr(), plan.split_tiles.data_ptr(),
                   plan.num.data_ptr(), plan.out_row.data_ptr(),

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--stats", type=int, default=1)
     ap.add_argument("--cluster", type=int, default=1, help="CTAs per cluster sharing B (1, 2, 4)")
     ap.add_argument("--detail", action="store_true", help="per-CTA breakdown of the slowest CTAs")
+    ap.add_argument("--fine", type=int, default=0, help="print the first N per-stage stamps of CTA 0")
     ap.add_argument("--only", default="", help="comma list of layer indices")
     a = ap.parse_args()
     import fusiontransformer_b200 as ft
@@ -104,7 +105,21 @@ def main():
         ops.OS_TRACE = []
         conv_engine.os_conv(x16, km, w, "forward", bn=bn)
         torch.cuda.synchronize()
-        tr = ops.OS_TRACE[0].cpu().numpy().astype(np.int64)
+ 
+        raw = ops.OS_TRACE[0].cpu().numpy().astype(np.int64)
+        tr, fine = raw[:148 * 8].reshape(148, 8), raw[148 * 8:]
+        if a.fine:
+            t00 = tr[0, 0]
+            st = fine[:2048].reshape(512, 4)
+            n = int((st[:, 0] > 0).sum())
+            print("      CTA 0 stages (us since CTA start): issued / landed / committed; landed-issued")
+            for i in range(min(n, a.fine)):
+                print("        stage %3d: %7.2f %7.2f %7.2f   fill %5.2f" % (
+                    i, (st[i, 0] - t00) / 1e3, (st[i, 1] - t00) / 1e3, (st[i, 2] - t00) / 1e3, (st[i, 1] - st[i, 0]) / 1e3))
+            un = fine[2048:2048 + 128].reshape(64, 2)
+            for i in range(int((un[:, 0] > 0).sum())):
+                print("        unit %2d: accumulator ready %7.2f rows written %7.2f" % (
+                    i, (un[i, 0] - t00) / 1e3, (un[i, 1] - t00) / 1e3))
         tr = tr[tr[:, 0] > 0]                    # CTAs that ran (the grid is min(tiles, 148))
         ops.OS_TRACE = None
         t0 = tr[:, 0]
