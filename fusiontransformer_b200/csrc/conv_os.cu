@@ -62,7 +62,9 @@ struct OsArgs {
   int unit_cap, K, kflip, red, ncols, nslots, tcols, nbuf;
   int cs, tile_rows;          // CTAs per cluster (1, 2, 4) and rows of a schedule tile (128 * cs)
   int dbg;                    // FT3D_OS_DEBUG, timing experiments only (results are then meaningless): 1 = no MMAs,
-                              // 2 = no A gathers, 4 = no B copies (tools/conv_os_probe.py --ablate)
+                              // 2 = no A gathers, 4 = no B copies (FT3D_OS_DEBUG=.. tools/conv_os_probe.py);
+                              // 8 = launch conv_os_kernel only, no fold / finalize (bench.py times the kernel alone
+                              // on repeats of a call whose complete form has already run)
 };
 
 __device__ __forceinline__ void os_cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
@@ -832,7 +834,7 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
     launch_pdl(conv_os_kernel<false, false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
   }
   int nparts = (int)grid;
-  if (scratch_slots > 0) {                       // the schedule has split tiles: fold their unit partials
+  if (scratch_slots > 0 && !(a.dbg & 8)) {       // the schedule has split tiles: fold their unit partials
     const int fgrid = (int)os_fold_ctas(scratch_slots);
     const int cv = ncols / 4;
     int ry = kColThreads / cv;
@@ -847,7 +849,7 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
                  num, out_row, (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
     nparts += fgrid * kOsFoldSlices;
   }
-  if (stats)
+  if (stats && !(a.dbg & 8))
     launch_pdl(col_finalize_kernel<0>, dim3(ncols / 4), dim3(kColThreads), 0, s, (const float*)a.partials, nparts,
                (int)ncols, n_out, eps, momentum, stat, running_mean, running_var, 0, valid_rows);
   return check_launch("ft3d_conv_os");
