@@ -76,18 +76,6 @@ __device__ __forceinline__ void os_cp_async_arrive_noinc(uint64_t* bar) {
 __device__ __forceinline__ void os_named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// true in exactly one lane of the (fully active) warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ unsigned long long os_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -333,7 +321,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
         uint8_t* st = smem + (size_t)slot * stage_bytes;
         if (fine != nullptr && tid == 0 && cnt < 512) fine[cnt * 4] = os_now();
-        if (elect_one()) {
+        if (elect_one_sync()) {
           if (warp == 0) {
             mbar_arrive_expect_tx(&hdr->full[slot], (uint32_t)(((a.dbg & 2) ? 0 : kBlockBytes) + ((a.dbg & 4) ? 0 : b_stage)));
             const uint8_t* bsrc = a.wpacked + ((size_t)k * nkb + kb) * b_bytes;
@@ -467,7 +455,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
             const uint64_t da0 = dhi | (uint64_t)((a_addr >> 4) & 0x3FFF);
             const uint64_t db0 = dhi | (uint64_t)(((a_addr + kBlockBytes) >> 4) & 0x3FFF);
             const int ksteps = (a.dbg & 1) ? 0 : ((red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4);
-            if (elect_one()) {
+            if (elect_one_sync()) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {             // one k-step = 16 bf16 = 32 bytes = 2 descriptor units
                 if (kk < ksteps) {
@@ -488,7 +476,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
             if (fine != nullptr && lane == 0 && cnt < 512) fine[cnt * 4 + 2] = os_now();
           }
         }
-        if (elect_one()) {
+        if (elect_one_sync()) {
           if (PAIR) umma_commit_pair(&hdr->acc_full[buf], cmask);
           else umma_commit(&hdr->acc_full[buf]);
         }

@@ -363,9 +363,11 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    {
       const uint32_t idesc = umma_idesc_bf16(128, ncols, 0, 0);
+      const uint64_t dhi = smem_desc_sw128(0, 16, 1024);
+      const uint32_t a_ring0 = smem_u32(a_ring), b_region0 = smem_u32(b_region);
       int cur_k = -1;
       uint32_t nb = 0, cnt = 0;
       TileCursor cur;
@@ -388,21 +390,29 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
           mbar_wait(&hdr->full_a[slot], use & 1);
           fence_proxy_async_smem();
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_ring + (size_t)slot * kBlockBytes);
-          const uint32_t b_addr = smem_u32(b_region + (size_t)kb * b_bytes);
+          const uint64_t da0 = dhi | (uint64_t)(((a_ring0 + (uint32_t)slot * (uint32_t)kBlockBytes) >> 4) & 0x3FFF);
+          const uint64_t db0 = dhi | (uint64_t)(((b_region0 + (uint32_t)kb * (uint32_t)b_bytes) >> 4) & 0x3FFF);
           const int ksteps = (red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4;
-          for (int kk = 0; kk < ksteps; ++kk)
-            umma_bf16(tmem_d, smem_desc_sw128(a_addr + kk * 32, 16, 1024), smem_desc_sw128(b_addr + kk * 32, 16, 1024),
-                      idesc, (kb | kk) != 0);
-          umma_commit(&hdr->empty_a[slot]);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              if (kk < ksteps) umma_bf16(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc, (kb | kk) != 0);
+            umma_commit(&hdr->empty_a[slot]);
+          }
+          __syncwarp();
         }
-        umma_commit(&hdr->acc_full[buf]);
         int nk = k;
+        bool last_of_k = false;
         if (g + 1 < g1) {
           cur.next();
           nk = cur.k;
-          if (nk != k) umma_commit(&hdr->b_free);
+          last_of_k = nk != k;
         }
+        if (elect_one_sync()) {
+          umma_commit(&hdr->acc_full[buf]);
+          if (last_of_k) umma_commit(&hdr->b_free);
+        }
+        __syncwarp();
         k = nk;
       }
     }
@@ -776,8 +786,13 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the units (uniform control flow keeps descriptors and barrier addresses in uniform
+    // registers) and one elected lane issues; from inside `if (lane == 0)` every tcgen05 instruction is wrapped in an
+    // elect / broadcast loop of ~30 dependent instructions (measured 165 ns per MMA in conv_os.cu).
+    {
       const uint32_t idesc = umma_idesc_bf16(128, cout, 1, 1);
+      const uint64_t dhi = smem_desc_sw128(0, kBlockBytes, 1024);
+      const uint32_t smem0 = smem_u32(smem);
       int group = -1, pk = -1, pmb = -1;
       UnitCursor uc;
       uc.seek(hdr->off, K, T, u0);
@@ -785,7 +800,8 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
         const int mb = uc.mb, k = uc.c.k;
         const bool fresh = (k != pk || mb != pmb);
         if (fresh) {
-          if (group >= 0) umma_commit(&hdr->acc_full[group & 1]);     // previous group complete -> flush warps
+          if (group >= 0 && elect_one_sync()) umma_commit(&hdr->acc_full[group & 1]);   // previous group -> flush warps
+          __syncwarp();
           ++group;
           const uint32_t ub = (uint32_t)group >> 1;
           if (ub > 0) mbar_wait(&hdr->acc_empty[group & 1], (ub & 1) ^ 1);
@@ -798,16 +814,20 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
         fence_proxy_async_smem();
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)((group & 1) * tcols);
-        const uint32_t a_addr = smem_u32(smem + (size_t)slot * stage_bytes);
-        const uint32_t b_addr = a_addr + a_blocks * kBlockBytes;
-        for (int kk = 0; kk < kTileRows / 16; ++kk) {
-          const uint64_t da = smem_desc_sw128(a_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
-          const uint64_t db = smem_desc_sw128(b_addr + kk * 16 * kBlockRowBytes, kBlockBytes, 1024);
-          umma_bf16(tmem_d, da, db, idesc, (!fresh || kk != 0) ? 1u : 0u);
+        const uint32_t a_addr = smem0 + (uint32_t)slot * (uint32_t)stage_bytes;
+        const uint64_t da0 = dhi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+        const uint64_t db0 = dhi | (uint64_t)(((a_addr + (uint32_t)(a_blocks * kBlockBytes)) >> 4) & 0x3FFF);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < kTileRows / 16; ++kk)       // 16 pairs = 16 rows of 128 bytes = 128 descriptor units
+            umma_bf16(tmem_d, da0 + (uint64_t)(kk * 16 * kBlockRowBytes >> 4), db0 + (uint64_t)(kk * 16 * kBlockRowBytes >> 4),
+                      idesc, (!fresh || kk != 0) ? 1u : 0u);
+          umma_commit(&hdr->empty[slot]);
         }
-        umma_commit(&hdr->empty[slot]);
+        __syncwarp();
       }
-      umma_commit(&hdr->acc_full[group & 1]);
+      if (elect_one_sync()) umma_commit(&hdr->acc_full[group & 1]);
+      __syncwarp();
     }
   } else if (warp >= 6) {
     // ------------------------------------------------------------------ flush

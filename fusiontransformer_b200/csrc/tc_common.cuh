@@ -20,6 +20,21 @@ constexpr int kBlockBytes = kTileRows * kBlockRowBytes; // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// true in exactly one lane of the (fully active) warp.  tcgen05 / TMA instructions take their operands from uniform
+// registers: issued under `if (elect_one_sync())` inside warp-uniform control flow they cost a few instructions, issued
+// under `if (lane == 0)` the compiler wraps each one in an elect / broadcast loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

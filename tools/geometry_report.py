@@ -37,7 +37,11 @@ def sizes(shape, batch=8):
 
 def main():
     shape, path = sys.argv[1], sys.argv[2]
-    line = [json.loads(l) for l in open(path) if l.startswith("{")][-1]
+    text = open(path).read()
+    try:
+        line = json.loads(text)                          # one (possibly indented) JSON object
+    except json.JSONDecodeError:
+        line = [json.loads(l) for l in text.splitlines() if l.startswith("{")][-1]      # a log with the JSON line in it
     ms = line["kernel_ms_per_step"]
     peak = 6547.5
     n_raw, lv = sizes(shape)
