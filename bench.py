@@ -593,12 +593,10 @@ def main():
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        if gstep is not None and in_graph and os.environ.get("FT3D_NCCL_TEARDOWN", "exit") == "exit":
-            # NCCL work captured in CUDA graphs: ProcessGroupNCCL's teardown waited for ever on this stack (torch 2.11,
-            # NCCL 2.28) although every collective had completed (the timings above were exchanged and read).  All
-            # results are out; leave without the teardown.  FT3D_NCCL_TEARDOWN=clean releases the graphs first and
-            # runs the regular teardown.
-            os._exit(0)
+        if os.environ.get("FT3D_NCCL_TEARDOWN", "clean") == "exit":
+            os._exit(0)        # escape hatch only: skip the process-group teardown
+        # NCCL work captured in CUDA graphs: the graphs (and the static buffers they reference) are released BEFORE the
+        # process group is destroyed -- destroying it first left ProcessGroupNCCL's teardown waiting on the captured work.
         if gstep is not None:
             gstep.graph = None
             gstep.static = None
