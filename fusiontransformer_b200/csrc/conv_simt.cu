@@ -122,6 +122,26 @@ conv_wgrad_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   }
 }
 
+// Deterministic variant (FT3D_DETERMINISTIC): a thread owns ONE element gw[k, ci, co] and walks all pairs of offset k
+// in list order -- no atomics, no workspace; slower (a serial walk of L_k pairs per thread), used for the exact-fp32
+// layers (the 4-channel stem in tensor-core mode).
+__global__ void __launch_bounds__(128)
+conv_wgrad_f32_det_kernel(const float* __restrict__ a, const float* __restrict__ b, const int2* __restrict__ pairs,
+                          const int32_t* __restrict__ off, int ca, int cin, int cout, float* __restrict__ gw) {
+  pdl_enter();
+  const int k = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cin * cout) return;
+  const int ci = e / cout, co = e - ci * cout;
+  const int begin = __ldg(off + k), end = __ldg(off + k + 1);
+  float s = 0.f;
+  for (int t = begin; t < end; ++t) {
+    const int2 p = __ldg(pairs + t);
+    s = fmaf(__ldg(a + (int64_t)(ca ? p.y : p.x) * cin + ci), __ldg(b + (int64_t)(ca ? p.x : p.y) * cout + co), s);
+  }
+  gw[((int64_t)k * cin + ci) * cout + co] += s;
+}
+
 }  // namespace ft3d
 
 using namespace ft3d;
@@ -149,6 +169,17 @@ int ft3d_conv_wgrad_f32(const float* a, const float* b, const int32_t* pairs, co
   launch_pdl(conv_wgrad_f32_kernel, dim3((unsigned)items), dim3(256), 0, (cudaStream_t)stream, a, b, (const int2*)pairs, pair_offsets,
                                                                             K, ca, cin, cout, gw);
   return check_launch("ft3d_conv_wgrad_f32");
+}
+
+int ft3d_conv_wgrad_f32_det(const float* a, const float* b, const int32_t* pairs, const int32_t* pair_offsets,
+                            int32_t K, int32_t ca, int32_t cin, int32_t cout, int64_t max_pairs, float* gw,
+                            ft3d_stream_t stream) {
+  if (max_pairs == 0) return FT3D_OK;
+  FT3D_REQUIRE(a && b && pairs && pair_offsets && gw && K > 0 && cin > 0 && cout > 0,
+               "ft3d_conv_wgrad_f32_det: bad arguments");
+  launch_pdl(conv_wgrad_f32_det_kernel, dim3((unsigned)((cin * cout + 127) / 128), (unsigned)K), dim3(128), 0,
+             (cudaStream_t)stream, a, b, (const int2*)pairs, pair_offsets, (int)ca, (int)cin, (int)cout, gw);
+  return check_launch("ft3d_conv_wgrad_f32_det");
 }
 
 }  // extern "C"

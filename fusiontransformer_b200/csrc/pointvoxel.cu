@@ -135,6 +135,44 @@ __global__ void devoxelize_bwd_kernel(const float* __restrict__ gout, const int3
   }
 }
 
+// ------------------------------------------------------------------ deterministic segmented sums (FT3D_DETERMINISTIC)
+// out[v,:] = sum over entries e in [off[v], off[v+1]), IN ENTRY ORDER, of  w[e] * src[row[e],:] (/ cnt[v] per term)
+// The scatter kernels above add their terms with fp32 atomics in arrival order (as the reference's own torchsparse
+// kernels do); here the caller has sorted the contributions by destination row (stable, so ascending source row)
+// and a thread group owns a destination row: a fixed summation order, bit-identical from run to run.
+template <int VEC>
+__global__ void segsum_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ entry_row,
+                                   const float* __restrict__ entry_w, const int32_t* __restrict__ off,
+                                   const int32_t* __restrict__ cnt, int64_t m, int c, float* __restrict__ out) {
+  pdl_enter();
+  const int cv = c / VEC;
+  const int64_t total = m * cv;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / cv;
+    const int ch = (int)(t - v * cv) * VEC;
+    const int e0 = __ldg(off + v), e1 = __ldg(off + v + 1);
+    const float den = cnt != nullptr ? (float)max(__ldg(cnt + v), 1) : 1.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = e0; e < e1; ++e) {
+      const int64_t r = __ldg(entry_row + e);
+      const float wk = entry_w != nullptr ? __ldg(entry_w + e) : 1.f;
+      if (VEC == 4) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src + r * c + ch));
+        if (cnt != nullptr) {
+          acc.x += __fdiv_rn(x.x, den); acc.y += __fdiv_rn(x.y, den); acc.z += __fdiv_rn(x.z, den); acc.w += __fdiv_rn(x.w, den);
+        } else {
+          acc.x += wk * x.x; acc.y += wk * x.y; acc.z += wk * x.z; acc.w += wk * x.w;
+        }
+      } else {
+        const float x = __ldg(src + r * c + ch);
+        acc.x += cnt != nullptr ? __fdiv_rn(x, den) : wk * x;
+      }
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(out + v * c + ch) = acc;
+    else out[v * c + ch] = acc.x;
+  }
+}
+
 // ------------------------------------------------------------------ K8 (API layout [8,n], idx int64)
 __device__ __forceinline__ float ti_weight(float x, float y, float z, float scale, int k) {
   float flx = (scale != 1.f) ? floorf(x / scale) * scale : floorf(x);
@@ -322,6 +360,18 @@ int ft3d_devoxelize_fwd(const float* feat, const int32_t* idx, const float* w, i
   else
     launch_pdl(devoxelize_fwd_kernel<1>, dim3(grid_for(n * c, 256)), dim3(256), 0, s, feat, idx, w, n, m, c, out);
   return check_launch("ft3d_devoxelize_fwd");
+}
+
+int ft3d_segsum_rows(const float* src, const int32_t* entry_row, const float* entry_w, const int32_t* offsets,
+                     const int32_t* cnt, int64_t m, int32_t c, float* out, ft3d_stream_t stream) {
+  if (m == 0) return FT3D_OK;
+  FT3D_REQUIRE(src && entry_row && offsets && out && c > 0 && !(entry_w && cnt), "ft3d_segsum_rows: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c % 4 == 0 && aligned16(src) && aligned16(out))
+    launch_pdl(segsum_rows_kernel<4>, dim3(grid_for(m * (c / 4), 256)), dim3(256), 0, s, src, entry_row, entry_w, offsets, cnt, m, (int)c, out);
+  else
+    launch_pdl(segsum_rows_kernel<1>, dim3(grid_for(m * c, 256)), dim3(256), 0, s, src, entry_row, entry_w, offsets, cnt, m, (int)c, out);
+  return check_launch("ft3d_segsum_rows");
 }
 
 int ft3d_devoxelize_bwd(const float* gout, const int32_t* idx, const float* w, int64_t n, int64_t m,

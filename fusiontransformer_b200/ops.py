@@ -199,6 +199,24 @@ def count(idx: torch.Tensor, m: int) -> torch.Tensor:
     return out
 
 
+def deterministic() -> bool:
+    """``FT3D_DETERMINISTIC=1``: every floating-point reduction of the training step runs in a fixed order -- the
+    point<->voxel scatter-adds as sorted segmented sums (``_segments`` + ``ft3d_segsum_rows``), the weight gradients as
+    two-stage / single-owner sums (``wgrad_deterministic``), BatchNorm sums and conv_os as always.  Two steps from the
+    same state give bit-identical gradients (tests/test_gpu_fidelity.py); slower, so opt-in."""
+    import os
+    return os.environ.get("FT3D_DETERMINISTIC", "0") not in ("0", "")
+
+
+def _segments(dest, m: int):
+    """CSR view of a scatter: ``dest`` int32 [E] destination row of every contribution (< 0 or >= m: dropped) ->
+    (order int32 [E]: contributions sorted by destination, stable; offsets int32 [m+1])."""
+    key = torch.where((dest < 0) | (dest >= m), torch.full_like(dest, m), dest)
+    skey, order = torch.sort(key, stable=True)
+    offsets = torch.searchsorted(skey, torch.arange(m + 1, dtype=skey.dtype, device=dest.device))
+    return order.to(torch.int32), offsets.to(torch.int32)
+
+
 def voxelize_fwd(feat, idx, cnt):
     feat = _chk(feat, torch.float32, "feat")
     idx = _chk(idx, torch.int32, "idx")
@@ -206,6 +224,11 @@ def voxelize_fwd(feat, idx, cnt):
     n, c = feat.shape
     m = cnt.numel()
     out = torch.empty((m, c), dtype=torch.float32, device=feat.device)
+    if deterministic() and n > 0 and m > 0:
+        order, offsets = _segments(idx, m)
+        lib().segsum_rows(feat.data_ptr(), order.data_ptr(), None, offsets.data_ptr(), cnt.data_ptr(), m, c,
+                          out.data_ptr(), _stream())
+        return out
     lib().voxelize_fwd(feat.data_ptr(), idx.data_ptr(), cnt.data_ptr(), n, m, c, out.data_ptr(), _stream())
     return out
 
@@ -233,6 +256,13 @@ def devoxelize_bwd(gout, idx, w, m):
     gout = _chk(gout, torch.float32, "gout")
     n, c = gout.shape
     gfeat = torch.empty((m, c), dtype=torch.float32, device=gout.device)
+    if deterministic() and n > 0 and m > 0:
+        order, offsets = _segments(idx.reshape(-1), m)          # contribution e = 8 * point + corner
+        rows = torch.div(order, 8, rounding_mode="floor").to(torch.int32)
+        wts = w.reshape(-1)[order.long()].contiguous()
+        lib().segsum_rows(gout.data_ptr(), rows.data_ptr(), wts.data_ptr(), offsets.data_ptr(), None, m, c,
+                          gfeat.data_ptr(), _stream())
+        return gfeat
     lib().devoxelize_bwd(gout.data_ptr(), idx.data_ptr(), w.data_ptr(), n, m, c, gfeat.data_ptr(), _stream())
     return gfeat
 
@@ -321,8 +351,9 @@ def conv_wgrad_f32(a, b, pairs, pair_offsets, k, ca, cin, cout, max_pairs):
     a = _chk(a, torch.float32, "a")
     b = _chk(b, torch.float32, "b")
     gw = torch.zeros((k, cin, cout), dtype=torch.float32, device=a.device)
-    lib().conv_wgrad_f32(a.data_ptr(), b.data_ptr(), pairs.data_ptr(), pair_offsets.data_ptr(), k, int(ca), cin,
-                         cout, int(max_pairs), gw.data_ptr(), _stream())
+    fn = lib().conv_wgrad_f32_det if deterministic() else lib().conv_wgrad_f32
+    fn(a.data_ptr(), b.data_ptr(), pairs.data_ptr(), pair_offsets.data_ptr(), k, int(ca), cin, cout, int(max_pairs),
+       gw.data_ptr(), _stream())
     return gw
 
 

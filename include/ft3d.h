@@ -116,6 +116,14 @@ int ft3d_devoxelize_fwd(const float* feat, const int32_t* idx, const float* w, i
                         int64_t m, int32_t c, float* out, ft3d_stream_t stream);
 int ft3d_devoxelize_bwd(const float* gout, const int32_t* idx, const float* w, int64_t n,
                         int64_t m, int32_t c, float* gfeat, ft3d_stream_t stream);
+/* Deterministic form of the two scatter-adds above (FT3D_DETERMINISTIC=1 in the Python boundary): the caller sorts the
+ * contributions by destination row (stable) and passes them as a CSR list; a thread group owns a destination row and
+ * adds its terms in list order -- no float atomics, bit-identical from run to run.
+ *   out[v,:] = sum_{e in [offsets[v], offsets[v+1])}  t(e),   t(e) = entry_w[e] * src[entry_row[e],:]   (cnt == NULL)
+ *                                                              t(e) = src[entry_row[e],:] / cnt[v]      (cnt != NULL)
+ * entry_row int32 [E], entry_w f32 [E] (nullable), offsets int32 [m+1], cnt int32 [m] (nullable), out f32 [m,c]. */
+int ft3d_segsum_rows(const float* src, const int32_t* entry_row, const float* entry_w, const int32_t* offsets,
+                     const int32_t* cnt, int64_t m, int32_t c, float* out, ft3d_stream_t stream);
 /* spf.calc_ti_weights: pc f32 [n,4], idx int64 [8,n] -> w_out f32 [8,n]. */
 int ft3d_ti_weights(const float* pc, const int64_t* idx, int64_t n, float scale, float* w_out,
                     ft3d_stream_t stream);
@@ -171,6 +179,11 @@ int ft3d_conv_pack_weights_multi(const void* desc, int32_t n_desc, int64_t total
 int ft3d_conv_wgrad_f32(const float* a, const float* b, const int32_t* pairs,
                         const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
                         int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
+/* Same result without atomics: one thread per element of gw walks the pairs of its offset in list order
+ * (bit-identical from run to run; slower). */
+int ft3d_conv_wgrad_f32_det(const float* a, const float* b, const int32_t* pairs,
+                            const int32_t* pair_offsets, int32_t K, int32_t ca, int32_t cin,
+                            int32_t cout, int64_t max_pairs, float* gw, ft3d_stream_t stream);
 
 /* Pair-major tensor-core path (the default): gather -> GEMM -> sorted, atomic-free scatter.
  *   ft3d_to_bf16        : activations / gradients rounded once to bf16 (dst holds n bf16).

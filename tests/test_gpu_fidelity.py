@@ -135,3 +135,73 @@ def test_tc_mode_trains_like_fp32_mode(monkeypatch):
     for lv, sf, st in hits:
         assert sf < steps and st < steps and abs(st - sf) <= max(6, 0.15 * sf), (lv, sf, st)
     assert abs(mt[-1] - mf[-1]) < 0.25 * mf[-1] + 2e-4        # same plateau
+
+
+def test_deterministic_mode_gives_bit_identical_steps(monkeypatch, small_batch):
+    """FT3D_DETERMINISTIC=1: the point<->voxel scatter-adds run as sorted segmented sums, the weight gradients as
+    two-stage / single-owner sums; conv_os and the BatchNorm sums are order-fixed anyway.  Two training steps from the
+    same state (tensor-core mode, fused blocks) give bit-identical loss, logits and parameter gradients -- and agree
+    with the default (atomic) mode to rounding."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200.fused import fuse, join_side_streams
+    from fusiontransformer_b200.spvcnn import Net3DSeg
+    coords, feats = small_batch["coords"].cuda(), small_batch["feats"].cuda()
+    n = coords.shape[0]
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(n, 96, generator=g).cuda()
+    labels = torch.randint(0, 20, (n,), generator=g).cuda()
+    monkeypatch.setenv("FT3D_CONV", "tc")
+    torch.manual_seed(1)
+    net = Net3DSeg(num_classes=20, dual_head=False, fusion="middle").cuda().train()
+    net.dropout.p = 0.0
+    fuse(net)
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+
+    def step():
+        net.load_state_dict(state)                       # running statistics too
+        for p in net.parameters():
+            p.grad = None
+        out = net(ft.SparseTensor(feats, coords), img)
+        loss = torch.nn.functional.cross_entropy(out["lidar_seg_logit"], labels)
+        loss.backward()
+        join_side_streams()
+        torch.cuda.synchronize()
+        return loss.detach().clone(), out["lidar_seg_logit"].detach().clone(), \
+            {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    monkeypatch.setenv("FT3D_DETERMINISTIC", "1")
+    la, za, ga = step()
+    lb, zb, gb = step()
+    assert torch.equal(la, lb) and torch.equal(za, zb)
+    for k in ga:
+        assert torch.equal(ga[k], gb[k]), k
+    monkeypatch.setenv("FT3D_DETERMINISTIC", "0")
+    lc, zc, gc = step()
+    assert abs(lc.item() - la.item()) < 1e-4 * abs(la.item())
+    a = torch.cat([v.flatten() for v in ga.values()]).double()
+    c = torch.cat([gc[k].flatten() for k in ga]).double()
+    assert (a @ c / (a.norm() * c.norm())).item() > 0.99       # same gradients up to summation order (+ chaos, DESIGN 2)
+
+
+@pytest.mark.parametrize("c", [4, 32, 96])
+def test_segmented_sums_match_the_atomic_scatters(monkeypatch, c):
+    """ft3d_segsum_rows (deterministic) against ft3d_voxelize_fwd / ft3d_devoxelize_bwd (atomic): same sums up to
+    summation order, with dropped (-1) contributions, empty voxels and repeated launches bit-identical."""
+    from fusiontransformer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(c)
+    n, m = 5000, 1300
+    idx = torch.randint(-1, m, (n,), device="cuda", generator=g, dtype=torch.int32)
+    cnt = torch.bincount(idx[idx >= 0].long(), minlength=m).int()
+    feat = torch.randn(n, c, device="cuda", generator=g)
+    monkeypatch.setenv("FT3D_DETERMINISTIC", "0")
+    want = ops.voxelize_fwd(feat, idx, cnt)
+    monkeypatch.setenv("FT3D_DETERMINISTIC", "1")
+    got = [ops.voxelize_fwd(feat, idx, cnt) for _ in range(2)]
+    assert torch.equal(got[0], got[1]) and (got[0] - want).abs().max() < 1e-5
+    idx8 = torch.randint(-1, m, (n, 8), device="cuda", generator=g, dtype=torch.int32)
+    w8 = torch.rand(n, 8, device="cuda", generator=g)
+    monkeypatch.setenv("FT3D_DETERMINISTIC", "0")
+    want = ops.devoxelize_bwd(feat, idx8, w8, m)
+    monkeypatch.setenv("FT3D_DETERMINISTIC", "1")
+    got = [ops.devoxelize_bwd(feat, idx8, w8, m) for _ in range(2)]
+    assert torch.equal(got[0], got[1]) and (got[0] - want).abs().max() < 1e-4 * max(1.0, want.abs().max().item())
