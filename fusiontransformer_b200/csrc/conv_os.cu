@@ -63,6 +63,7 @@ struct OsArgs {
   int cs, tile_rows;          // CTAs per cluster (1, 2, 4) and rows of a schedule tile (128 * cs)
   int dbg;                    // FT3D_OS_DEBUG, timing experiments only (results are then meaningless): 1 = no MMAs,
                               // 2 = no A gathers, 4 = no B copies (FT3D_OS_DEBUG=.. tools/conv_os_probe.py);
+                              // 16 = alternate the accumulator of consecutive MMAs (are dependent MMAs serialised?)
                               // 8 = launch conv_os_kernel only, no fold / finalize (bench.py times the kernel alone
                               // on repeats of a call whose complete form has already run)
 };
@@ -461,6 +462,8 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
                 if (kk < ksteps) {
                   const uint32_t acc = (uint32_t)((q | kb | kk) != 0);
                   if (PAIR) umma_bf16_pair(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
+                  else if ((a.dbg & 16) && a.nbuf == 2)     // timing experiment: consecutive MMAs into different accumulators
+                    umma_bf16(tmem_base + (uint32_t)(((buf ^ (kk & 1)) * a.tcols)), da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
                   else umma_bf16(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
                   if (nsplit == 2) {
                     if (PAIR) umma_bf16_pair(tmem_d + (uint32_t)ncw, da0 + 2 * kk, db0 + c_step + 2 * kk, idesc, acc);
