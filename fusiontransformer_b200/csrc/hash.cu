@@ -120,6 +120,72 @@ __global__ void scale_coords_kernel(const float* __restrict__ pts, const int32_t
   }
 }
 
+// ------------------------------------------------------------------ a1 with the augmentation branch
+// data/utils/augmentation_3d.py:22-51.  The random numbers are drawn on the host in the reference's order (they are a
+// dozen per scan); the device applies them to every point with numpy's float32 arithmetic: the [n,3] x [3,3] product
+// as sgemm evaluates it (rounded product, then two fused multiply-adds, k ascending -- verified bit-exact against
+// numpy/OpenBLAS), scale, per-scan minimum, and the translation offset computed in float64 from the float32 extent.
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v == 0.f) v = 0.f;
+  if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v));
+  else atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+
+__device__ __forceinline__ float aug_coord(const float* __restrict__ pts, int64_t i, const float* __restrict__ rot, int s,
+                                           int d, float scale) {
+  float v = pts[i * 3 + d];
+  if (rot != nullptr) {
+    const float* r = rot + s * 9;
+    v = __fmul_rn(pts[i * 3], r[d]);
+    v = __fmaf_rn(pts[i * 3 + 1], r[3 + d], v);
+    v = __fmaf_rn(pts[i * 3 + 2], r[6 + d], v);
+  }
+  return __fmul_rn(v, scale);
+}
+
+__global__ void scan_minmax_kernel(const float* __restrict__ pts, const int32_t* __restrict__ scan_id, int64_t n,
+                                   float scale, const float* __restrict__ rot, float* __restrict__ mins,
+                                   float* __restrict__ maxs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = scan_id[i];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = aug_coord(pts, i, rot, s, d, scale);
+      atomic_min_float(mins + s * 3 + d, v);
+      atomic_max_float(maxs + s * 3 + d, v);
+    }
+  }
+}
+
+__global__ void augment_scale_kernel(const float* __restrict__ pts, const int32_t* __restrict__ scan_id, int64_t n,
+                                     float scale, int full_scale, const float* __restrict__ rot,
+                                     const double* __restrict__ transl_u, const float* __restrict__ mins,
+                                     const float* __restrict__ maxs, int4* __restrict__ coords,
+                                     uint8_t* __restrict__ keep) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = scan_id[i];
+    int c[3];
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float mn = mins[s * 3 + d];
+      float v = __fsub_rn(aug_coord(pts, i, rot, s, d, scale), mn);                   // :43, :46
+      if (transl_u != nullptr) {
+        // :50-51  offset = clip(full_scale - coords.max(0) - 0.001, 0) * rand(3): float32 up to the product with the
+        // float64 draw; coords += offset is evaluated in float64 and rounded back to float32
+        const float mx = __fsub_rn(maxs[s * 3 + d], mn);                               // max of the shifted column
+        float room = __fsub_rn(__fsub_rn((float)full_scale, mx), 0.001f);
+        room = room > 0.f ? room : 0.f;
+        v = (float)((double)v + (double)room * transl_u[s * 3 + d]);
+      }
+      c[d] = (int)v;
+      ok = ok && (c[d] >= 0) && (c[d] < full_scale);
+    }
+    coords[i] = make_int4(c[0], c[1], c[2], s);
+    keep[i] = ok ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------ K10 helper
 __device__ __forceinline__ int floor_to(int v, int r) {
   // torch: floor(floor(float(v)/r)*r); coordinates are < 2^24 so the float path is exact
@@ -218,6 +284,23 @@ int ft3d_scale_coords(const float* points, const int32_t* scan_id, int64_t n, in
   scale_coords_kernel<<<grid_for(n, 256), 256, 0, s>>>(points, scan_id, n, scale, full_scale, min_ws,
                                                        (int4*)coords_out, keep_out);
   return check_launch("ft3d_scale_coords");
+}
+
+int ft3d_augment_scale_coords(const float* points, const int32_t* scan_id, int64_t n, int32_t num_scans, float scale,
+                              int32_t full_scale, const float* rot, const double* transl_u, int32_t* coords_out,
+                              uint8_t* keep_out, float* ws, ft3d_stream_t stream) {
+  if (n == 0) return FT3D_OK;
+  FT3D_REQUIRE(points && scan_id && coords_out && keep_out && ws && num_scans > 0,
+               "ft3d_augment_scale_coords: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* mins = ws;
+  float* maxs = ws + (int64_t)num_scans * 3;
+  fill_f32_kernel<<<1, 256, 0, s>>>(mins, (int64_t)num_scans * 3, INFINITY);
+  fill_f32_kernel<<<1, 256, 0, s>>>(maxs, (int64_t)num_scans * 3, -INFINITY);
+  scan_minmax_kernel<<<grid_for(n, 256), 256, 0, s>>>(points, scan_id, n, scale, rot, mins, maxs);
+  augment_scale_kernel<<<grid_for(n, 256), 256, 0, s>>>(points, scan_id, n, scale, full_scale, rot, transl_u, mins, maxs,
+                                                        (int4*)coords_out, keep_out);
+  return check_launch("ft3d_augment_scale_coords");
 }
 
 int ft3d_coarsen_hash(const int32_t* coords, int64_t n, int32_t ratio, int32_t* coarse_out,

@@ -101,13 +101,29 @@ def unique_sorted(keys: torch.Tensor):
     return uniq[:m], inverse, counts[:m], first[:m]
 
 
-def scale_coords(points: torch.Tensor, scan_id: torch.Tensor, num_scans: int, scale: float, full_scale: int):
+def scale_coords(points: torch.Tensor, scan_id: torch.Tensor, num_scans: int, scale: float, full_scale: int,
+                 rot: torch.Tensor | None = None, transl_u: torch.Tensor | None = None):
+    """a1.  ``rot`` f32 [num_scans,3,3] / ``transl_u`` f64 [num_scans,3] (device): the per-scan draws of the
+    augmentation branch (utils/augment.py), applied with numpy's arithmetic by ``ft3d_augment_scale_coords``."""
     points = _chk(points, torch.float32, "points")
     scan_id = _chk(scan_id, torch.int32, "scan_id")
     n = points.shape[0]
     dev = points.device
     coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
     keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    if rot is not None or transl_u is not None:
+        if rot is not None:
+            rot = _chk(rot, torch.float32, "rot")
+            if tuple(rot.shape) != (num_scans, 3, 3):
+                raise Ft3dError("scale_coords: rot must be [num_scans, 3, 3]")
+        if transl_u is not None:
+            transl_u = _chk(transl_u, torch.float64, "transl_u")
+            if tuple(transl_u.shape) != (num_scans, 3):
+                raise Ft3dError("scale_coords: transl_u must be [num_scans, 3]")
+        ws = torch.empty(num_scans * 6, dtype=torch.float32, device=dev)
+        lib().augment_scale_coords(points.data_ptr(), scan_id.data_ptr(), n, num_scans, float(scale), int(full_scale),
+                                   _p(rot), _p(transl_u), coords.data_ptr(), keep.data_ptr(), ws.data_ptr(), _stream())
+        return coords, keep.bool()
     mins = torch.empty(num_scans * 3, dtype=torch.float32, device=dev)
     lib().scale_coords(points.data_ptr(), scan_id.data_ptr(), n, num_scans, float(scale), int(full_scale),
                        coords.data_ptr(), keep.data_ptr(), mins.data_ptr(), _stream())

@@ -69,12 +69,13 @@ def sparse_quantize(coords, feats=None, labels=None, ignore_label=-100, return_i
 
 
 def sparse_quantize_batch(points: torch.Tensor, scan_id: torch.Tensor, num_scans: int, scale: float = 20.0,
-                          full_scale: int = 4096):
+                          full_scale: int = 4096, rot: torch.Tensor | None = None, transl_u: torch.Tensor | None = None):
     """Device-side a1+a2+a3 for a whole batch: raw points [n,3] f32 in metres with
     their scan ids (ascending, contiguous) -> (coords int32 [m,4] after the bounds filter, kept row ids [m],
     unique first-occurrence rows [U] into the kept set ordered by (scan, key), inverse [m], per-scan counts).
-    Follows data/utils/augmentation_3d.py:43-46 and semantic_kitti_dataloader.py:220-231 without augmentation."""
-    coords, keep = ops.scale_coords(points, scan_id, num_scans, scale, full_scale)
+    Follows data/utils/augmentation_3d.py:43-46 and semantic_kitti_dataloader.py:220-231; ``rot`` / ``transl_u`` (the
+    per-scan draws of utils/augment.py) switch the augmentation branch (:22-41, :48-51) on."""
+    coords, keep = ops.scale_coords(points, scan_id, num_scans, scale, full_scale, rot=rot, transl_u=transl_u)
     kept = torch.nonzero(keep).flatten()
     vc = coords[kept].contiguous()
     inds, invs, scan_counts = ops.quantize(vc, num_scans)

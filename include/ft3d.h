@@ -43,6 +43,14 @@ int ft3d_kernel_hash(const int32_t* coords, int64_t n, const int32_t* offsets, i
 int ft3d_scale_coords(const float* points, const int32_t* scan_id, int64_t n, int32_t num_scans,
                       float scale, int32_t full_scale, int32_t* coords_out, uint8_t* keep_out,
                       float* min_ws, ft3d_stream_t stream);
+/* The same with the augmentation branch (data/utils/augmentation_3d.py:22-41,48-51).  The caller draws the random
+ * numbers on the host in the reference's order (a dozen per scan) and passes them: rot f32 [num_scans,3,3] (nullable:
+ * no rotation; p' = p . rot evaluated as numpy's float32 sgemm does), transl_u f64 [num_scans,3] (nullable: the
+ * uniform factors of the random translation; offset = clip(full_scale - max - 0.001, 0) * u in float64, added into the
+ * float32 coordinate).  ws f32 [num_scans*6] scratch (per-scan minima and maxima). */
+int ft3d_augment_scale_coords(const float* points, const int32_t* scan_id, int64_t n, int32_t num_scans,
+                              float scale, int32_t full_scale, const float* rot, const double* transl_u,
+                              int32_t* coords_out, uint8_t* keep_out, float* ws, ft3d_stream_t stream);
 
 /* ---- a2 / K15  torchsparse.utils.sparse_quantize (semantic_kitti_dataloader.py:231) ------- */
 /* coords int32 [n,4] (x,y,z,scan), scans contiguous and ascending.  Per scan: unique 64-bit

@@ -38,6 +38,42 @@ def voxelize_scan(points: np.ndarray, scale: int = 20, full_scale: int = 4096):
     return vc, keep, inds, inv
 
 
+def augment_draws(noisy_rot=0.0, flip_x=0.0, flip_y=0.0, rot_z=0.0, transl=False, rng=np.random):
+    """The random numbers of one call of augmentation_3d.py:22-51, drawn in the reference's order from ``rng`` (the
+    global numpy generator by default, as the reference uses it): -> (rot float32 [3,3] | None, u float64 [3] | None)
+    with ``u`` the uniform factors of the random translation (they are drawn AFTER the rotation's numbers; the offset
+    itself depends on the rotated points, see ``augment_and_scale``)."""
+    rot = None
+    if noisy_rot > 0 or flip_x > 0 or flip_y > 0 or rot_z > 0:
+        rot = np.eye(3, dtype=np.float32)
+        if noisy_rot > 0:                       # :25-26  noise on every element (float64 draws added into the f32 matrix)
+            rot += rng.randn(3, 3) * noisy_rot
+        if flip_x > 0:                          # :28-29  sign of the x axis
+            rot[0][0] *= rng.randint(0, 2) * 2 - 1
+        if flip_y > 0:                          # :31-32
+            rot[1][1] *= rng.randint(0, 2) * 2 - 1
+        if rot_z > 0:                           # :34-39  rotation about the up axis, composed on the right
+            theta = rng.rand() * rot_z
+            rz = np.array([[np.cos(theta), -np.sin(theta), 0], [np.sin(theta), np.cos(theta), 0], [0, 0, 1]],
+                          dtype=np.float32)
+            rot = rot.dot(rz)
+    u = rng.rand(3) if transl else None         # :50
+    return rot, u
+
+
+def augment_and_scale(points: np.ndarray, scale, full_scale, rot=None, u=None):
+    """augmentation_3d.py:40-51 given the draws of ``augment_draws``: rotate (float32 matrix product), scale, move to
+    the positive octant, optionally translate inside the receptive field.  Returns float32 coordinates [n,3]."""
+    if rot is not None:
+        points = points.dot(rot)                # :40
+    coords = points * scale                     # :43
+    coords -= coords.min(0)                     # :46
+    if u is not None:                           # :48-51 (float64 offset added into the float32 array)
+        offset = np.clip(full_scale - coords.max(0) - 0.001, a_min=0, a_max=None) * u
+        coords += offset
+    return coords
+
+
 def collate(scans):
     """collate.py:36-67: append the batch index column and concatenate.
 

@@ -40,6 +40,31 @@ def gen_ref_voxelize():
     return out
 
 
+def gen_ref_augment():
+    """a1 with the augmentation branch on (augmentation_3d.py:22-51; the values of the commented-out training configs,
+    config/FusionTransformerConfig.py:44-47,66-69): the reference function under a seeded global numpy generator."""
+    sys.path.insert(0, REF)
+    from FusionTransformer.data.utils.augmentation_3d import augment_and_scale_3d
+    from fusiontransformer_b200.synthetic import make_scan
+    out = {}
+    cases = (("a", "nuscenes", 7, 101, dict(noisy_rot=0.1, flip_x=0.5, rot_z=6.2831, transl=True)),
+             ("b", "nuscenes", 8, 202, dict(noisy_rot=0.1, flip_y=0.5, rot_z=6.2831, transl=True)),
+             ("c", "nuscenes", 9, 303, dict(rot_z=6.2831)),
+             ("d", "nuscenes", 10, 404, dict(transl=True)))
+    for tag, shape, sid, seed, kw in cases:
+        pts = make_scan(shape, sid)["points"][:3000].copy()
+        np.random.seed(seed)
+        coords_f = augment_and_scale_3d(pts, 20, 4096, **kw)
+        coords = coords_f.astype(np.int64)
+        idxs = (coords.min(1) >= 0) * (coords.max(1) < 4096)
+        out.update({tag + "_points": pts, tag + "_seed": np.int64(seed), tag + "_coords_float": coords_f,
+                    tag + "_coords": coords.astype(np.int32), tag + "_keep": idxs})
+        for k in ("noisy_rot", "flip_x", "flip_y", "rot_z"):
+            out[tag + "_" + k] = np.float64(kw.get(k, 0.0))
+        out[tag + "_transl"] = np.bool_(kw.get("transl", False))
+    return out
+
+
 def gen_ref_segiou():
     sys.path.insert(0, REF)
     from FusionTransformer.data.utils.validate import map_sparse_to_org
@@ -89,7 +114,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_voxelize.npz"), **gen_ref_voxelize())
     np.savez_compressed(os.path.join(HERE, "ref_segiou.npz"), **gen_ref_segiou())
     np.savez_compressed(os.path.join(HERE, "ref_collate.npz"), **gen_ref_collate())
-    for f in ("ref_voxelize.npz", "ref_segiou.npz", "ref_collate.npz"):
+    np.savez_compressed(os.path.join(HERE, "ref_augment.npz"), **gen_ref_augment())
+    for f in ("ref_voxelize.npz", "ref_segiou.npz", "ref_collate.npz", "ref_augment.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

@@ -148,6 +148,44 @@ def test_device_voxelization_matches_reference_augment_and_scale(tag):
 
 
 @pytest.mark.gpu
+def test_device_augmentation_matches_reference_augment_and_scale():
+    """a1 with the augmentation branch on, on the GPU: four scans with four different parameter sets in ONE batch
+    (ft3d_augment_scale_coords with the host-side draws of utils/augment.py) against the reference function run on each
+    scan under the same seed -- voxel coordinates and bounds mask bit-exact."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import ops
+    from fusiontransformer_b200.utils import augment
+    g = np.load(os.path.join(GOLD, "ref_augment.npz"))
+    tags = ["a", "b", "c", "d"]
+    pts, sid, rots, us = [], [], [], []
+    for i, tag in enumerate(tags):
+        kw = dict(noisy_rot=float(g[tag + "_noisy_rot"]), flip_x=float(g[tag + "_flip_x"]), flip_y=float(g[tag + "_flip_y"]),
+                  rot_z=float(g[tag + "_rot_z"]), transl=bool(g[tag + "_transl"]))
+        np.random.seed(int(g[tag + "_seed"]))
+        rot, u = augment.draw(**kw)
+        rots.append(np.eye(3, dtype=np.float32) if rot is None else rot)          # identity: exact under the fma chain
+        us.append(np.zeros(3) if u is None else u)                                # zero factor: no translation
+        pts.append(g[tag + "_points"])
+        sid.append(np.full(len(pts[-1]), i, np.int32))
+    points = torch.from_numpy(np.concatenate(pts)).cuda()
+    scan_id = torch.from_numpy(np.concatenate(sid)).cuda()
+    rot = torch.from_numpy(np.stack(rots)).cuda()
+    tu = torch.from_numpy(np.stack(us)).cuda()
+    coords, keep = ops.scale_coords(points, scan_id, len(tags), 20.0, 4096, rot=rot, transl_u=tu)
+    coords, keep = coords.cpu().numpy(), keep.cpu().numpy()
+    o = 0
+    for i, tag in enumerate(tags):
+        n = len(pts[i])
+        np.testing.assert_array_equal(coords[o:o + n, :3], g[tag + "_coords"], err_msg=tag)
+        np.testing.assert_array_equal(coords[o:o + n, 3], i)
+        np.testing.assert_array_equal(keep[o:o + n], g[tag + "_keep"], err_msg=tag)
+        o += n
+    # and through the batch API: same coordinates after the bounds filter
+    vc, kept, inds, inv, counts = ft.utils.sparse_quantize_batch(points, scan_id, len(tags), rot=rot, transl_u=tu)
+    np.testing.assert_array_equal(vc.cpu().numpy(), coords[keep])
+
+
+@pytest.mark.gpu
 def test_device_seg_iou_matches_reference_metric_fixture():
     """(f)4: losses.SegIoU against FusionTransformer/models/metric.py:SegIoU run by the reference on the same data."""
     from fusiontransformer_b200.losses import SegIoU

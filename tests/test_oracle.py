@@ -238,6 +238,35 @@ def test_oracle_voxelize_matches_reference_augment_and_scale(tag):
     np.testing.assert_array_equal(vc[inds][inv], vc)      # a2 round trip on the reference's coordinates
 
 
+def _aug_params(g, tag):
+    return dict(noisy_rot=float(g[tag + "_noisy_rot"]), flip_x=float(g[tag + "_flip_x"]), flip_y=float(g[tag + "_flip_y"]),
+                rot_z=float(g[tag + "_rot_z"]), transl=bool(g[tag + "_transl"]))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_oracle_augmentation_matches_reference_augment_and_scale(tag):
+    """a1 with the augmentation branch on (augmentation_3d.py:22-51): the oracle's restatement, and the product's
+    host-side draws (utils/augment.py), against the reference function run under the same seeded numpy generator --
+    bit-identical float32 coordinates, identical draws."""
+    from fusiontransformer_b200.utils import augment
+    from oracle import ft_glue as og
+    g = np.load(os.path.join(GOLD, "ref_augment.npz"))
+    kw = _aug_params(g, tag)
+    np.random.seed(int(g[tag + "_seed"]))
+    rot, u = og.augment_draws(**kw)
+    coords = og.augment_and_scale(g[tag + "_points"].copy(), 20, 4096, rot, u)
+    assert coords.dtype == np.float32
+    np.testing.assert_array_equal(coords, g[tag + "_coords_float"])
+    np.random.seed(int(g[tag + "_seed"]))
+    rot_p, u_p = augment.draw(**kw)
+    assert (rot is None) == (rot_p is None) and (u is None) == (u_p is None)
+    if rot is not None:
+        assert rot_p.dtype == np.float32
+        np.testing.assert_array_equal(rot_p, rot)
+    if u is not None:
+        np.testing.assert_array_equal(u_p, u)
+
+
 def test_oracle_unmap_matches_reference_map_sparse_to_org():
     from oracle import ft_glue as og
     g = np.load(os.path.join(GOLD, "ref_segiou.npz"))
