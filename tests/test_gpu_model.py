@@ -132,3 +132,48 @@ def test_logits_match_reference_run_fixture(monkeypatch, fusion, mode, tol):
     if mode == "f32":
         assert rel_l2(m.linear.weight.grad, torch.from_numpy(gold[fusion + "_grad_linear_weight"])) < 2e-3
         assert rel_l2(m.up4[1][1].net[3].kernel.grad, torch.from_numpy(gold[fusion + "_grad_up4_last_kernel"])) < 2e-3
+
+
+@pytest.mark.parametrize("mode,tol", [("f32", 2e-4), ("tc", 1e-2)])
+def test_configs0_kitti_scan_forward_matches_cpu_oracle(monkeypatch, mode, tol):
+    """BASELINE.json configs[0]: ONE SemanticKITTI-shaped synthetic scan (~20 k front-camera points, 0.05 m voxels),
+    single forward of the 3D UNet + middle fusion, batch 1 -- the reference's CPU-runnable case.  The CPU oracle's
+    forward (timed, printed) is the expected output; the device path runs a1-a3 on the GPU (dataflow) and must give
+    the same voxels and, per point, the same logits."""
+    import time
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import dataflow
+    from fusiontransformer_b200.synthetic import make_scan
+    from oracle import ft_glue as og, ts_ops as ts
+    monkeypatch.setenv("FT3D_CONV", mode)
+    monkeypatch.setattr(ts, "OPERAND_DTYPE", "bf16" if mode == "tc" else None)
+    scan = make_scan("kitti", 41)
+    o, m = _models("middle", seed=5)
+    o.eval(), m.eval()
+    # CPU: the reference pipeline (a1-a3 + model) restated by the oracle
+    vc, keep, inds, inv = og.voxelize_scan(scan["points"])
+    st = og.collate([dict(coords=vc[inds], feats=scan["feats"][keep][inds])])
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(st.C.shape[0], 96, generator=g)
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        lo = o(ts.SparseTensor(st.F, st.C), img)["lidar_seg_logit"]
+    t_cpu = time.perf_counter() - t0
+    # GPU: device voxelization of the raw scan, then the model
+    db = dataflow.to_device(dataflow.host_batch_from_scans([scan]), torch.device("cuda", 0))
+    lidar, rc, bidx, labels, ginv, kept = dataflow.voxelize_batch(db)
+    assert torch.equal(lidar.C.cpu().long(), st.C.long())                  # same voxels, same order (bit-exact a1-a3)
+    with torch.no_grad():
+        for _ in range(2):                                                 # one-time set-up (library, workspaces, images)
+            m(ft.SparseTensor(lidar.F, lidar.C), img.cuda())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lg = m(ft.SparseTensor(lidar.F, lidar.C), img.cuda())["lidar_seg_logit"]   # fresh tensor: maps rebuilt, eager
+        torch.cuda.synchronize()
+    t_gpu = time.perf_counter() - t0
+    print("\nconfigs[0] (%d points -> %d voxels), single forward: CPU oracle %.3f s on %d threads, B200 %.2f ms [%s]"
+          % (len(scan["points"]), st.C.shape[0], t_cpu, torch.get_num_threads(), 1e3 * t_gpu, mode))
+    assert 15000 < len(scan["points"]) < 30000
+    assert rel_l2(lg, lo) < tol
+    assert (lg.argmax(1).cpu() == lo.argmax(1)).float().mean() > 0.97
