@@ -11,16 +11,22 @@
 // CTA to finish turns the partials into this layer's BatchNorm training statistics (mean, rstd, running stats): the
 // activation is never re-read for its statistics and no finalize kernel is launched.
 //
-// Warp roles (320 threads, one persistent CTA per SM, tiles t = blockIdx.x, += gridDim.x):
-//   0      producer, TMA mode (default): the 32 lanes issue 32 x cp.async.bulk.tensor.2d ... tile::gather4 (4 rows x
-//          128 B each, hardware 128B swizzle, out-of-range row index -1 => zero fill) = one 128 x 64 A block, and lane 0
-//          adds the cp.async.bulk of the matching B block onto the same mbarrier (complete_tx bytes);
-//   0-3,4  producers, LDGSTS mode (FT3D_OS_GATHER=ldgsts): 16-byte cp.async row pieces + bulk B, as conv_pairs_tc.cu;
-//   5      MMA issuer: tcgen05.mma 128 x ncols x 16 into accumulator buffer (tile & 1); tcgen05.commit frees ring
-//          slots and hands the accumulator to the epilogue;
-//   6-9    epilogue: tcgen05.ld -> per-warp staging transpose -> 128-byte row segments to out[row] + statistics.
-// The A/B ring runs across pass and tile boundaries; two TMEM accumulators (ncols <= 256) let the gathers and MMAs
-// of tile t+1 run under the epilogue of tile t.
+// Warp roles ((NPW + 6) warps, one persistent CTA per SM, units dealt round by round; NPW = 4 or 8 gather warps):
+//   0..NPW-1  TMA gather warps: each issues 32/NPW x cp.async.bulk.tensor.2d ... tile::gather4 per stage (4 rows x 128 B,
+//             hardware 128B swizzle, row index -1 => zero fill); together one 128 x 64 A block;
+//   NPW       weight loader: arms the stage's mbarrier with the byte count and issues the cp.async.bulk of B_k;
+//             (LDGSTS mode, FT3D_OS_GATHER=ldgsts, NPW = 4: warps 0-3 issue 16-byte cp.async row pieces instead)
+//   NPW+1     MMA issuer: tcgen05.mma 128 x ncols x 16 into accumulator buffer (unit & 1); tcgen05.commit frees ring
+//             slots and hands the accumulator to the epilogue;
+//   NPW+2..5  epilogue: tcgen05.ld -> per-warp staging transpose -> 128-byte row segments to out[row] + statistics.
+// The A/B ring runs across pass and unit boundaries; two TMEM accumulators (ncols <= 256) let the gathers and MMAs
+// of unit u+1 run under the epilogue of unit u.
+//
+// Every role is ONE warp walking the schedule serially, so the instructions a role spends per stage bound the kernel
+// long before the tensor pipe or L2 do (a stage is only 4 MMAs of 16-128 cycles each).  The loops are therefore kept
+// to a few dozen instructions per stage: ring slot / phase are counters (no division), the four k-steps of a stage
+// are ONE asm block (descriptor low words advance by +2, predicates instead of branches), everything that only the
+// timing experiments need (FT3D_OS_DEBUG, the trace stamps) is compiled into a separate DBG instantiation.
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
@@ -30,11 +36,11 @@
 namespace ft3d {
 using namespace tc;
 
-constexpr int kOsThreads = 320;
 constexpr int kOsMaxSlots = 10;
+constexpr int kOsDefaultGatherWarps = 8;       // TMA gather warps per CTA unless FT3D_OS_PRODUCERS says otherwise
 constexpr int kOsStageFloats = 32 * 36;        // one epilogue warp: 32 rows x (32 + 4 pad) floats
-constexpr int kOsProducers = 128;              // warps 0-3
-constexpr int kOsAhead = 4;                    // passes whose indices are in flight in a TMA producer warp
+constexpr int kOsProducers = 128;              // LDGSTS mode: warps 0-3
+constexpr int kOsAhead = 4;                    // passes whose indices are in flight in a TMA gather warp
 
 struct OsHeader {
   uint64_t full[kOsMaxSlots];
@@ -214,10 +220,133 @@ struct OsPassIter {
   }
 };
 
-template <bool TMA, bool PAIR>
-__global__ void __launch_bounds__(kOsThreads)
+// ---- barrier operations on shared-window addresses (the role loops keep &full[0] / &empty[0] as 32-bit bases)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITA_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAITA_DONE;\n"
+      "bra WAITA_LOOP;\n"
+      "WAITA_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_a(uint32_t bar, uint32_t parity) {   // pairs with a remote arrive
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITCA_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAITCA_DONE;\n"
+      "bra WAITCA_LOOP;\n"
+      "WAITCA_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                     uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_gather4_a(uint32_t dst_smem, const CUtensorMap* tmap, int col, int r0, int r1, int r2,
+                                              int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst_smem),
+      "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_a(uint32_t bar, int cs, uint16_t cmask) {
+  if (PAIR)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cmask)
+                 : "memory");
+  else if (cs == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cmask)
+                 : "memory");
+}
+
+// One stage = one 64-wide k-block = up to four k-steps of 16: D (+)= A[128 x 16] * B[n x 16]^T, k-step kk reads the
+// operands 32 bytes (2 descriptor units) further along the swizzled rows.  a_lo / b_lo are the LOW words of the
+// shared-memory descriptors (start >> 4 | LBO field), desc_hi the constant high word; `acc_first` = 0 overwrites the
+// accumulator with the first k-step (first stage of a unit).  One straight-line block, the k-steps beyond `ksteps`
+// predicated off: between two MMAs the issuing warp executes two adds and two moves on uniform registers.
+#define FT3D_OS_KBLOCK_ASM(GROUP)                                                      \
+  asm volatile(                                                                        \
+      "{\n"                                                                            \
+      ".reg .pred p0, pt, q0, q1, q2, q3;\n"                                           \
+      ".reg .b64 da, db;\n"                                                            \
+      ".reg .b32 al, bl;\n"                                                            \
+      "setp.ne.b32 p0, %5, 0;\n"                                                       \
+      "setp.ge.u32 pt, %6, 0;\n"                                                       \
+      "setp.gt.u32 q0, %6, 0;\n"                                                       \
+      "setp.gt.u32 q1, %6, 1;\n"                                                       \
+      "setp.gt.u32 q2, %6, 2;\n"                                                       \
+      "setp.gt.u32 q3, %6, 3;\n"                                                       \
+      "mov.b64 da, {%1, %3};\n"                                                        \
+      "mov.b64 db, {%2, %3};\n"                                                        \
+      "@q0 tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %4, p0;\n"         \
+      "add.u32 al, %1, 2;\n"                                                           \
+      "add.u32 bl, %2, 2;\n"                                                           \
+      "mov.b64 da, {al, %3};\n"                                                        \
+      "mov.b64 db, {bl, %3};\n"                                                        \
+      "@q1 tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %4, pt;\n"         \
+      "add.u32 al, %1, 4;\n"                                                           \
+      "add.u32 bl, %2, 4;\n"                                                           \
+      "mov.b64 da, {al, %3};\n"                                                        \
+      "mov.b64 db, {bl, %3};\n"                                                        \
+      "@q2 tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %4, pt;\n"         \
+      "add.u32 al, %1, 6;\n"                                                           \
+      "add.u32 bl, %2, 6;\n"                                                           \
+      "mov.b64 da, {al, %3};\n"                                                        \
+      "mov.b64 db, {bl, %3};\n"                                                        \
+      "@q3 tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %4, pt;\n"         \
+      "}\n" ::"r"(tmem_d),                                                             \
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc_first), "r"(ksteps)      \
+      : "memory")
+template <bool PAIR>
+__device__ __forceinline__ void umma_bf16_kblock(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                 uint32_t idesc, uint32_t acc_first, uint32_t ksteps) {
+  if (PAIR) FT3D_OS_KBLOCK_ASM("2");
+  else FT3D_OS_KBLOCK_ASM("1");
+}
+#undef FT3D_OS_KBLOCK_ASM
+
+// ring position of a role: slot index and the number of completed trips round the ring (-> barrier parities)
+struct OsRing {
+  uint32_t slot, round, nslots;
+  __device__ __forceinline__ void init(int n) { slot = 0; round = 0; nslots = (uint32_t)n; }
+  __device__ __forceinline__ void advance() {
+    if (++slot == nslots) { slot = 0; ++round; }
+  }
+};
+
+template <bool TMA, bool PAIR, int NPW, bool DBG>
+__global__ void __launch_bounds__((NPW + 6) * 32)
 conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   static_assert(TMA || !PAIR, "CTA pairs use the TMA gather");
+  static_assert(NPW == 4 || NPW == 8, "4 or 8 gather warps");
+  static_assert(TMA || NPW == 4, "LDGSTS mode has four producer warps");
+  constexpr int kLoaderWarp = NPW, kMmaWarp = NPW + 1, kEpiWarp0 = NPW + 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int red = a.red, ncols = a.ncols, nslots = a.nslots;
@@ -234,6 +363,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   const int step = (int)gridDim.x / cs, first = (int)blockIdx.x / cs;      // units are dealt to clusters
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   const int row_base = rank * kTileRows;                                   // this CTA's slice of a schedule tile
+  const int dbg = DBG ? a.dbg : 0;
 
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
@@ -262,94 +392,131 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
   const uint32_t tmem_base = hdr->tmem_base;
   int U = __ldg(a.num + 1);
   if (U > a.unit_cap) U = a.unit_cap;
-  unsigned long long* tr = a.trace != nullptr ? a.trace + (size_t)blockIdx.x * 8 : nullptr;
-  if (tr != nullptr && tid == 0) tr[0] = os_now();
+  unsigned long long* tr = (DBG && a.trace != nullptr) ? a.trace + (size_t)blockIdx.x * 8 : nullptr;
+  if (DBG && tr != nullptr && tid == 0) tr[0] = os_now();
   // per-stage stamps of CTA 0 behind the per-CTA records: [stage][4] = {issued, landed, MMAs committed, -} for the first
   // 512 stages, then [unit][2] = {accumulator ready, rows written} from offset 2048 (tools/conv_os_probe.py --fine)
-  unsigned long long* fine = (a.trace != nullptr && blockIdx.x == 0) ? a.trace + (size_t)kNumSMs * 8 : nullptr;
+  unsigned long long* fine = (DBG && a.trace != nullptr && blockIdx.x == 0) ? a.trace + (size_t)kNumSMs * 8 : nullptr;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&hdr->full[0]), empty0 = smem_u32(&hdr->empty[0]);
 
-  if (TMA && warp < 4) {
-    // ------------------------------------------------------------------ producers: TMA gather4 (A) + bulk copy (B)
-    // A 128 x 64 block is 32 gather4 loads; a warp issues them lane by lane (the operands of a TMA instruction are
-    // warp-uniform), so the four producer warps each take a quarter of the block: lanes 0-7 of warp w load rows
-    // w*32 + 4*lane .. +3.  Warp 0 also arms the stage's mbarrier with the byte count and adds the B block.
-    // The offset and the gather indices of a pass are requested kOsAhead passes before they are needed: a narrow layer
-    // issues a pass in ~0.2 us, far less than a loaded L2 round trip, so a one-pass look-ahead left the producers
-    // waiting for indices (0.6-0.7 us per pass measured on the 32- and 64-channel layers).
+  if (TMA && warp < NPW) {
+    // ------------------------------------------------------------------ gather warps: TMA gather4 (A)
+    // A 128 x 64 block is 32 gather4 loads; a warp issues them one by one (the operands of a TMA instruction are
+    // warp-uniform), so the NPW gather warps each take 32/NPW of them: lanes 0..G-1 of warp w hold the indices of rows
+    // (w*G + lane)*4 .. +3.  The loads complete on the stage's mbarrier, which the weight loader arms with the byte
+    // count (a transaction count may run negative until then: only the loader's arrival can complete the phase).
+    // The gather indices of a pass are requested kOsAhead passes before they are needed: a narrow layer issues a pass
+    // in ~0.2 us, far less than a loaded L2 round trip.
+    constexpr int G = 32 / NPW;
     OsPassIter it;
     it.init(a.units, U, first, step);
-    const int sub = lane & 7;
-    int kq[kOsAhead];
+    const int sub = lane & (G - 1);
     int4 rq[kOsAhead];
     int queued = 0;
 #pragma unroll
     for (int d = 0; d < kOsAhead; ++d) {
-      kq[d] = 0;
       rq[d] = make_int4(-1, -1, -1, -1);
       if (it.valid()) {
-        kq[d] = __ldg(a.pass_k + it.pass());
-        rq[d] = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
+        rq[d] = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * G + sub);
         it.next();
         ++queued;
       }
     }
+    OsRing ring;
+    ring.init(nslots);
+    const uint32_t dst0 = smem0 + (uint32_t)(warp * G) * 512u;
     uint32_t cnt = 0, npass = 0;
     while (queued > 0) {
 #pragma unroll
-     for (int d = 0; d < kOsAhead; ++d) {
-      if (queued == 0) break;
-      const int k = a.kflip ? a.K - 1 - kq[d] : kq[d];
-      const int4 r4 = rq[d];
-      --queued;
-      ++npass;
-      if (it.valid()) {                                    // refill the slot just consumed: pass + kOsAhead
+      for (int d = 0; d < kOsAhead; ++d) {
+        if (queued == 0) break;
+        const int4 r4 = rq[d];
+        --queued;
+        if (DBG) ++npass;
+        if (it.valid()) {                                    // refill the slot just consumed: pass + kOsAhead
+          rq[d] = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * G + sub);
+          it.next();
+          ++queued;
+        }
+        // every lane walks the loop (uniform control flow: the TMA operands are built in uniform registers) and one
+        // elected lane issues; the row indices come from lanes 0..G-1
+        int rr[G][4];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          rr[i][0] = __shfl_sync(0xffffffffu, r4.x, i); rr[i][1] = __shfl_sync(0xffffffffu, r4.y, i);
+          rr[i][2] = __shfl_sync(0xffffffffu, r4.z, i); rr[i][3] = __shfl_sync(0xffffffffu, r4.w, i);
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (ring.round > 0) mbar_wait_a(empty0 + 8u * ring.slot, (ring.round & 1) ^ 1);
+          if (DBG && fine != nullptr && tid == 0 && cnt < 512) fine[cnt * 4] = os_now();
+          if (DBG) ++cnt;
+          if (!(DBG && (dbg & 2)) && elect_one_sync()) {
+            const uint32_t dst = dst0 + ring.slot * (uint32_t)stage_bytes;
+            const uint32_t bar = full0 + 8u * ring.slot;
+#pragma unroll
+            for (int i = 0; i < G; ++i)
+              tma_gather4_a(dst + (uint32_t)i * 512u, &tmap, kb * 64, rr[i][0], rr[i][1], rr[i][2], rr[i][3], bar);
+          }
+          __syncwarp();
+          ring.advance();
+        }
+      }
+    }
+    if (DBG && tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = npass;
+  } else if (TMA && warp == kLoaderWarp) {
+    // ------------------------------------------------------------------ weight loader: expect_tx + bulk copy of B_k
+    OsPassIter it;
+    it.init(a.units, U, first, step);
+    int kq[kOsAhead];
+    int queued = 0;
+#pragma unroll
+    for (int d = 0; d < kOsAhead; ++d) {
+      kq[d] = 0;
+      if (it.valid()) {
         kq[d] = __ldg(a.pass_k + it.pass());
-        rq[d] = __ldg(reinterpret_cast<const int4*>(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base) + warp * 8 + sub);
         it.next();
         ++queued;
       }
-      // the eight gather4 of this warp take their row indices from lanes 0-7; every lane walks the loop (uniform
-      // control flow: the TMA operands are built in uniform registers) and one elected lane issues
-      int rr[8][4];
+    }
+    OsRing ring;
+    ring.init(nslots);
+    const uint32_t tx = (uint32_t)(((DBG && (dbg & 2)) ? 0 : kBlockBytes) + ((DBG && (dbg & 4)) ? 0 : b_stage));
+    const int nsp = ncols > 256 ? 2 : 1;
+    const uint32_t half = (uint32_t)((ncols / nsp / 2) * kBlockRowBytes);   // pairs: this CTA's columns of one MMA's N range
+    while (queued > 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        rr[i][0] = __shfl_sync(0xffffffffu, r4.x, i); rr[i][1] = __shfl_sync(0xffffffffu, r4.y, i);
-        rr[i][2] = __shfl_sync(0xffffffffu, r4.z, i); rr[i][3] = __shfl_sync(0xffffffffu, r4.w, i);
-      }
-      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-        const int slot = (int)(cnt % (uint32_t)nslots);
-        const uint32_t use = cnt / (uint32_t)nslots;
-        if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
-        uint8_t* st = smem + (size_t)slot * stage_bytes;
-        if (fine != nullptr && tid == 0 && cnt < 512) fine[cnt * 4] = os_now();
-        if (elect_one_sync()) {
-          if (warp == 0) {
-            mbar_arrive_expect_tx(&hdr->full[slot], (uint32_t)(((a.dbg & 2) ? 0 : kBlockBytes) + ((a.dbg & 4) ? 0 : b_stage)));
-            const uint8_t* bsrc = a.wpacked + ((size_t)k * nkb + kb) * b_bytes;
-            if (a.dbg & 4) {
+      for (int d = 0; d < kOsAhead; ++d) {
+        if (queued == 0) break;
+        const int k = a.kflip ? a.K - 1 - kq[d] : kq[d];
+        --queued;
+        if (it.valid()) {
+          kq[d] = __ldg(a.pass_k + it.pass());
+          it.next();
+          ++queued;
+        }
+        const uint8_t* bsrc = a.wpacked + (size_t)k * nkb * b_bytes;
+        for (int kb = 0; kb < nkb; ++kb, bsrc += b_bytes) {
+          if (ring.round > 0) mbar_wait_a(empty0 + 8u * ring.slot, (ring.round & 1) ^ 1);
+          if (elect_one_sync()) {
+            const uint32_t bar = full0 + 8u * ring.slot;
+            const uint32_t dst = smem0 + ring.slot * (uint32_t)stage_bytes + (uint32_t)kBlockBytes;
+            mbar_expect_tx_a(bar, tx);
+            if (DBG && (dbg & 4)) {
             } else if (PAIR) {        // columns [c*ncw + rank*ncw/2, +ncw/2) of each MMA's N range: this CTA's half
-              const int nsp = ncols > 256 ? 2 : 1;
-              const int half = (ncols / nsp / 2) * kBlockRowBytes;
               for (int c = 0; c < nsp; ++c)
-                bulk_g2s(st + kBlockBytes + c * half, bsrc + (size_t)(2 * c + rank) * half, (uint32_t)half, &hdr->full[slot]);
+                bulk_g2s_a(dst + (uint32_t)c * half, bsrc + (size_t)(2 * c + rank) * half, half, bar);
             } else if (cs == 1) {
-              bulk_g2s(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot]);
+              bulk_g2s_a(dst, bsrc, (uint32_t)b_bytes, bar);
             } else if (rank == 0) {   // one L2 read for the whole cluster; every CTA's full[slot] gets its complete_tx
-              bulk_g2s_multicast(st + kBlockBytes, bsrc, (uint32_t)b_bytes, &hdr->full[slot], cmask);
+              bulk_g2s_multicast_a(dst, bsrc, (uint32_t)b_bytes, bar, cmask);
             }
           }
-          if (!(a.dbg & 2)) {
-            const uint32_t dst = smem_u32(st) + (uint32_t)(warp * 8) * 512u;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              tma_gather4(dst + (uint32_t)i * 512u, &tmap, kb * 64, rr[i][0], rr[i][1], rr[i][2], rr[i][3], &hdr->full[slot]);
-          }
+          __syncwarp();
+          ring.advance();
         }
-        __syncwarp();
       }
-     }
     }
-    if (tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = npass;
   } else if (!TMA && warp < 4) {
     // ------------------------------------------------------------------ producers: 16-byte cp.async row pieces
     OsPassIter it;
@@ -380,8 +547,8 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         os_cp_async_arrive_noinc(&hdr->full[slot]);
       }
     }
-    if (tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = np;
-  } else if (!TMA && warp == 4) {
+    if (DBG && tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = np;
+  } else if (!TMA && warp == kLoaderWarp) {
     // ------------------------------------------------------------------ weight loader (LDGSTS mode)
     if (lane == 0) {
       OsPassIter it;
@@ -400,35 +567,40 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (PAIR && rank != 0) {
       // rank 1 of a pair: tell rank 0's MMA issuer when this CTA's half of a stage has landed
       if (lane == 0) {
-        uint32_t cnt = 0;
+        OsRing ring;
+        ring.init(nslots);
         int np_n = first < U ? __ldg(a.units + 2 * (int64_t)first).y : 0;
         for (int u = first; u < U; u += step) {
           const int np = np_n;
           if (u + step < U) np_n = __ldg(a.units + 2 * (int64_t)(u + step)).y;
-          for (int q = 0; q < np * nkb; ++q, ++cnt) {
-            const int slot = (int)(cnt % (uint32_t)nslots);
-            mbar_wait(&hdr->full[slot], (cnt / (uint32_t)nslots) & 1);
-            mbar_arrive_remote(&hdr->pfull[slot], 0);
+          for (int q = 0; q < np * nkb; ++q) {
+            mbar_wait_a(full0 + 8u * ring.slot, ring.round & 1);
+            mbar_arrive_remote(&hdr->pfull[ring.slot], 0);
+            ring.advance();
           }
         }
       }
     } else {
       // All 32 lanes walk the schedule together and ONE elected lane issues: with uniform control flow the shared-
-      // memory descriptors, TMEM addresses and barrier addresses live in uniform registers, so an MMA costs a handful
-      // of instructions.  (Issued from inside an `if (lane == 0)` region the compiler wraps every tcgen05 instruction
-      // in an elect/broadcast loop: ~30 dependent instructions per MMA, measured 165 ns per MMA whatever its N.)
+      // memory descriptors, TMEM addresses and barrier addresses live in uniform registers.  (Issued from inside an
+      // `if (lane == 0)` region the compiler wraps every tcgen05 instruction in an elect/broadcast loop: ~30 dependent
+      // instructions per MMA, measured 165 ns per MMA whatever its N.)
       const int nsplit = ncols > 256 ? 2 : 1;
       const int ncw = ncols / nsplit;
       const int b_rows = PAIR ? ncw / 2 : ncw;             // rows of one MMA's B operand held by this CTA
       const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ncw, 0, 0);
-      const uint64_t dhi = smem_desc_sw128(0, 16, 1024);   // descriptor without its start address
-      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t dfull = smem_desc_sw128(0, 16, 1024); // descriptor without its start address
+      const uint32_t desc_hi = (uint32_t)(dfull >> 32), desc_lo0 = (uint32_t)dfull;
       const uint32_t c_step = (uint32_t)(b_rows * kBlockRowBytes) >> 4;
+      const uint32_t pfull0 = smem_u32(&hdr->pfull[0]);
+      const uint32_t last_ksteps = (uint32_t)((red - (nkb - 1) * 64) >> 4);   // k-steps of the last (maybe partial) k-block
+      OsRing ring;
+      ring.init(nslots);
       uint32_t cnt = 0, use_acc = 0;
       int np_n = first < U ? __ldg(a.units + 2 * (int64_t)first).y : 0;
       for (int u = first; u < U; u += step) {
@@ -443,56 +615,41 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * a.tcols);
+        uint32_t acc = 0;                                              // the unit's first k-step overwrites
         for (int q = 0; q < np; ++q) {
-          for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-            const int slot = (int)(cnt % (uint32_t)nslots);
-            const uint32_t use = cnt / (uint32_t)nslots;
-            mbar_wait(&hdr->full[slot], use & 1);
-            if (PAIR) mbar_wait_cluster(&hdr->pfull[slot], use & 1);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait_a(full0 + 8u * ring.slot, ring.round & 1);
+            if (PAIR) mbar_wait_cluster_a(pfull0 + 8u * ring.slot, ring.round & 1);
             if (!TMA) fence_proxy_async_smem();            // cp.async (generic proxy) data -> tensor-core reads
             tc_fence_after();
-            if (fine != nullptr && lane == 0 && cnt < 512) fine[cnt * 4 + 1] = os_now();
-            const uint32_t a_addr = smem0 + (uint32_t)slot * (uint32_t)stage_bytes;
-            const uint64_t da0 = dhi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-            const uint64_t db0 = dhi | (uint64_t)(((a_addr + kBlockBytes) >> 4) & 0x3FFF);
-            const int ksteps = (a.dbg & 1) ? 0 : ((red - kb * 64 < 64 ? red - kb * 64 : 64) >> 4);
+            if (DBG && fine != nullptr && lane == 0 && cnt < 512) fine[cnt * 4 + 1] = os_now();
+            const uint32_t a_lo = desc_lo0 | ((smem0 + ring.slot * (uint32_t)stage_bytes) >> 4);
+            const uint32_t b_lo = a_lo + (uint32_t)(kBlockBytes >> 4);
+            uint32_t ksteps = kb == nkb - 1 ? last_ksteps : 4u;
+            if (DBG && (dbg & 1)) ksteps = 0;
             if (elect_one_sync()) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {             // one k-step = 16 bf16 = 32 bytes = 2 descriptor units
-                if (kk < ksteps) {
-                  const uint32_t acc = (uint32_t)((q | kb | kk) != 0);
-                  if (PAIR) umma_bf16_pair(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
-                  else if ((a.dbg & 16) && a.nbuf == 2)     // timing experiment: consecutive MMAs into different accumulators
-                    umma_bf16(tmem_base + (uint32_t)(((buf ^ (kk & 1)) * a.tcols)), da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
-                  else umma_bf16(tmem_d, da0 + 2 * kk, db0 + 2 * kk, idesc, acc);
-                  if (nsplit == 2) {
-                    if (PAIR) umma_bf16_pair(tmem_d + (uint32_t)ncw, da0 + 2 * kk, db0 + c_step + 2 * kk, idesc, acc);
-                    else umma_bf16(tmem_d + (uint32_t)ncw, da0 + 2 * kk, db0 + c_step + 2 * kk, idesc, acc);
-                  }
-                }
-              }
-              if (PAIR) umma_commit_pair(&hdr->empty[slot], cmask);
-              else if (cs == 1) umma_commit(&hdr->empty[slot]);
-              else umma_commit_multicast(&hdr->empty[slot], cmask);
+              umma_bf16_kblock<PAIR>(tmem_d, a_lo, b_lo, desc_hi, idesc, acc, ksteps);
+              if (nsplit == 2) umma_bf16_kblock<PAIR>(tmem_d + (uint32_t)ncw, a_lo, b_lo + c_step, desc_hi, idesc, acc, ksteps);
+              umma_commit_a<PAIR>(empty0 + 8u * ring.slot, cs, cmask);
             }
             __syncwarp();
-            if (fine != nullptr && lane == 0 && cnt < 512) fine[cnt * 4 + 2] = os_now();
+            acc = 1;
+            if (DBG && fine != nullptr && lane == 0 && cnt < 512) fine[cnt * 4 + 2] = os_now();
+            if (DBG) ++cnt;
+            ring.advance();
           }
         }
-        if (elect_one_sync()) {
-          if (PAIR) umma_commit_pair(&hdr->acc_full[buf], cmask);
-          else umma_commit(&hdr->acc_full[buf]);
-        }
+        if (elect_one_sync()) umma_commit_a<PAIR>(smem_u32(&hdr->acc_full[buf]), 1, cmask);
         __syncwarp();
         ++use_acc;
       }
-      if (tr != nullptr && lane == 0) tr[2] = os_now();
+      if (DBG && tr != nullptr && lane == 0) tr[2] = os_now();
     }
-  } else if (warp >= 6) {
+  } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue (TMEM quadrant = warp % 4)
-    const int q = warp & 3, te = tid - 6 * 32;
-    float* st = staging + (size_t)(warp - 6) * kOsStageFloats;
-    float* ws1 = sstat + (size_t)(warp - 6) * 2 * ncols;
+    const int q = warp & 3, te = tid - kEpiWarp0 * 32;
+    float* st = staging + (size_t)(warp - kEpiWarp0) * kOsStageFloats;
+    float* ws1 = sstat + (size_t)(warp - kEpiWarp0) * 2 * ncols;
     float* ws2 = ws1 + ncols;
     const bool stats = a.partials != nullptr;
     if (stats)
@@ -708,6 +865,45 @@ static bool os_pair_mode() {       // 256-row tiles: cta_group::2 pairs (default
   return e == nullptr || e[0] != '0';
 }
 
+static int os_gather_warps() {    // FT3D_OS_PRODUCERS = 4 | 8 TMA gather warps per CTA (read per call)
+  const char* e = getenv("FT3D_OS_PRODUCERS");
+  if (e != nullptr && e[0] == '4') return 4;
+  if (e != nullptr && e[0] == '8') return 8;
+  return kOsDefaultGatherWarps;
+}
+
+typedef void (*OsKernelFn)(const CUtensorMap, const OsArgs);
+struct OsVariant {
+  bool tma, pair;
+  int npw;
+  bool dbg;
+  OsKernelFn fn;
+};
+#define FT3D_OS_V(T, P, N, D) {T, P, N, D, conv_os_kernel<T, P, N, D>}
+static const OsVariant kOsVariants[] = {
+    FT3D_OS_V(true, false, 4, false),  FT3D_OS_V(true, false, 8, false),  FT3D_OS_V(true, true, 4, false),
+    FT3D_OS_V(true, true, 8, false),   FT3D_OS_V(false, false, 4, false), FT3D_OS_V(true, false, 4, true),
+    FT3D_OS_V(true, false, 8, true),   FT3D_OS_V(true, true, 4, true),    FT3D_OS_V(true, true, 8, true),
+    FT3D_OS_V(false, false, 4, true),
+};
+#undef FT3D_OS_V
+static const OsVariant* os_variant(bool tma, bool pair, int npw, bool dbg) {
+  for (const OsVariant& v : kOsVariants)
+    if (v.tma == tma && v.pair == pair && v.npw == npw && v.dbg == dbg) return &v;
+  return nullptr;
+}
+static cudaError_t os_configure() {          // once per process: opt in to 227 KB of dynamic shared memory
+  static cudaError_t state = cudaErrorUnknown;
+  if (state == cudaErrorUnknown) {
+    state = cudaSuccess;
+    for (const OsVariant& v : kOsVariants) {
+      cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) state = e;
+    }
+  }
+  return state;
+}
+
 constexpr int kOsMaxCtas = kNumSMs;
 
 constexpr int kOsFoldSlices = 4;                 // CTAs per split tile in the fold kernel
@@ -794,36 +990,34 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
   } else {
     memset(&tm, 0, sizeof(tm));
   }
-  static int configured = 0;
-  if (!configured) {
-    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FT3D_CUDA(cudaFuncSetAttribute(conv_os_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 1;
-  }
+  const int npw = tma ? os_gather_warps() : 4;
+  const bool dbgk = (a.dbg & ~8) != 0 || a.trace != nullptr;     // timing experiments / trace: the DBG instantiation
+  const OsVariant* v = os_variant(tma, pair, npw, dbgk);
+  FT3D_REQUIRE(v != nullptr, "ft3d_conv_os: no kernel variant");
+  FT3D_CUDA(os_configure());
   cudaStream_t s = (cudaStream_t)stream;
-  if (a.cs > 1) {                  // thread-block clusters: the CTAs of a cluster share every B block (multicast)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kOsThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)a.cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (pair) cudaLaunchKernelEx(&cfg, conv_os_kernel<true, true>, tm, a);
-    else cudaLaunchKernelEx(&cfg, conv_os_kernel<true, false>, tm, a);
-  } else if (tma) {
-    launch_pdl(conv_os_kernel<true, false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
-  } else {
-    launch_pdl(conv_os_kernel<false, false>, dim3(grid), dim3(kOsThreads), smem_bytes, s, tm, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((unsigned)((npw + 6) * 32));
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (a.cs > 1) {                  // thread-block clusters: CTA pairs (cta_group::2) or B multicast
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)a.cs;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaLaunchKernelEx(&cfg, v->fn, tm, a);
   int nparts = (int)grid;
   if (scratch_slots > 0 && !(a.dbg & 8)) {       // the schedule has split tiles: fold their unit partials
     const int fgrid = (int)os_fold_ctas(scratch_slots);
