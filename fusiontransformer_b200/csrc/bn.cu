@@ -31,11 +31,13 @@ __device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
 template <int RB>
 __global__ void __launch_bounds__(kColThreads)
 bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_per_cta,
-                float* __restrict__ partials, const int32_t* __restrict__ valid_rows) {
+                float* __restrict__ partials, const int32_t* __restrict__ valid_rows,
+                const float* __restrict__ pivot) {
   pdl_enter();
   __shared__ float4 s_stage[kColStageFloat4];
   n = effective_rows(n, valid_rows);
   const int ch = threadIdx.x * 4;
+  const float4 pv = stat_pivot(pivot, ch);
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row1 = row0 + rows_per_cta < n ? row0 + rows_per_cta : n;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
@@ -46,10 +48,8 @@ bn_stats_kernel(const float* __restrict__ y, int64_t n, int channels, int rows_p
     for (int i = 0; i < RB; ++i)
       v[i] = r + i * rstep < row1 ? ld4(y + (r + i * rstep) * channels + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      add4(s1, v[i]);
-      fma4(s2, v[i], v[i]);
-    }
+    for (int i = 0; i < RB; ++i)
+      if (r + i * rstep < row1) stat_add(s1, s2, v[i], pv);
   }
   col_publish(s1, s2, partials, channels, s_stage);
 }
@@ -250,11 +250,11 @@ int ft3d_bn_stats(const float* y, int64_t n, int32_t channels, float eps, float 
   ColGrid g = col_grid(n, channels / 4);
   switch (row_batch()) {
     case 1: launch_pdl(bn_stats_kernel<1>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
-                                                                valid_rows); break;
+                                                                valid_rows, (const float*)running_mean); break;
     case 2: launch_pdl(bn_stats_kernel<2>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
-                                                                valid_rows); break;
+                                                                valid_rows, (const float*)running_mean); break;
     default: launch_pdl(bn_stats_kernel<4>, dim3(g.grid), dim3(g.block), 0, (cudaStream_t)stream, y, n, channels, g.rows_per_cta, (float*)workspace,
-                                                                valid_rows); break;
+                                                                valid_rows, (const float*)running_mean); break;
   }
   launch_pdl(col_finalize_kernel<0>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream, (const float*)workspace, g.grid, channels, n, eps, momentum, stat, running_mean, running_var, 0, valid_rows);
   return check_launch("ft3d_bn_stats");
@@ -268,7 +268,7 @@ int ft3d_col_sum(const float* x, int64_t n, int32_t channels, float* out, int32_
   FT3D_REQUIRE(workspace_bytes >= col_workspace_bytes(channels), "ft3d_col_sum: workspace too small");
   ColGrid g = col_grid(n, channels / 4);
   launch_pdl(bn_stats_kernel<2>, dim3(g.grid), g.block, 0, (cudaStream_t)stream, x, n, channels, g.rows_per_cta,
-             (float*)workspace, (const int32_t*)nullptr);
+             (float*)workspace, (const int32_t*)nullptr, (const float*)nullptr);
   launch_pdl(col_finalize_kernel<2>, dim3(channels / 4), dim3(kColThreads), 0, (cudaStream_t)stream,
              (const float*)workspace, g.grid, channels, n, 0.f, 0.f, out, (float*)nullptr, (float*)nullptr, accumulate,
              (const int32_t*)nullptr);

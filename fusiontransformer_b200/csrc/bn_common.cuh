@@ -57,6 +57,21 @@ __device__ __forceinline__ void fma4(float4& a, const float4& b, const float4& c
   a.x = fmaf(b.x, c.x, a.x); a.y = fmaf(b.y, c.y, a.y); a.z = fmaf(b.z, c.z, a.z); a.w = fmaf(b.w, c.w, a.w);
 }
 
+// BatchNorm statistics are accumulated as SHIFTED sums  s1 = sum (y - p), s2 = sum (y - p)^2  with the per-channel pivot
+// p = the layer's running mean as it stands before this batch (0 without running statistics):  mean = p + s1/n,
+// var = s2/n - (s1/n)^2.  E[y^2] - mean^2 on raw fp32 sums loses everything once |mean| >> std (mean 100, std 0.1:
+// the variance drowns in the rounding of sum y^2); shifted by a pivot within a few std of the mean the subtraction is
+// harmless.  Every producer of statistics partial rows (conv_os epilogue and fold, conv_reduce, bn_stats) and the
+// finalize use the same pivot pointer; the finalize reads it before it updates the running mean.
+__device__ __forceinline__ float4 stat_pivot(const float* __restrict__ pivot, int ch) {
+  return pivot != nullptr ? __ldg(reinterpret_cast<const float4*>(pivot + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void stat_add(float4& s1, float4& s2, const float4& v, const float4& pv) {
+  const float4 d = make_float4(v.x - pv.x, v.y - pv.y, v.z - pv.z, v.w - pv.w);
+  add4(s1, d);
+  fma4(s2, d, d);
+}
+
 // Fold (s1, s2) over the row lanes of the CTA and publish the CTA's partial row: partials[cta][0][C], [cta][1][C].
 // `s_stage` must hold 2 * blockDim.x * blockDim.y float4.
 __device__ __forceinline__ void col_publish(float4 s1, float4 s2, float* __restrict__ partials, int channels,
@@ -136,8 +151,10 @@ col_finalize_kernel(const float* __restrict__ partials, int nparts, int channels
     const int c = c0 + t;
     const double s1 = s_acc[0][t], s2 = s_acc[0][4 + t];
     if (MODE == 0) {
-      const double mean = s1 / (double)n;
-      double var = s2 / (double)n - mean * mean;
+      // shifted sums (stat_add): pivot = the running mean before this batch
+      const double dm = s1 / (double)n;
+      const double mean = (out1 != nullptr ? (double)out1[c] : 0.0) + dm;
+      double var = s2 / (double)n - dm * dm;
       if (var < 0.0) var = 0.0;
       out0[c] = (float)mean;
       out0[channels + c] = (float)(1.0 / sqrt(var + (double)eps));

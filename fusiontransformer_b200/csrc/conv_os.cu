@@ -63,6 +63,7 @@ struct OsArgs {
   float* partials;            // statistics: [gridDim.x][2][ncols]; nullptr = no statistics
   float* scratch;             // [S][128][ncols] partial tiles of split tiles (folded by conv_os_fold_kernel)
   const int32_t* valid_rows;
+  const float* pivot;         // statistics: per-channel shift of the sums (the running mean; bn_common.cuh), nullable
   unsigned long long* trace;  // nullable: per CTA 8 x u64 (globaltimer stamps and counts), tools/conv_os_probe.py
   int64_t n_out;
   int unit_cap, K, kflip, red, ncols, nslots, tcols, nbuf;
@@ -696,6 +697,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
                                                                        __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         __syncwarp();
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        const float4 pv = stats ? stat_pivot(a.pivot, c0 + (lane & 7) * 4) : s1;
 #pragma unroll
         for (int i8 = 0; i8 < 8; ++i8) {                   // a warp store = 4 rows x 128 contiguous bytes
           const int r = i8 * 4 + (lane >> 3);
@@ -705,9 +707,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
             *reinterpret_cast<float4*>(part + (size_t)r * ncols + c0 + (lane & 7) * 4) = val;
           } else if (row >= 0) {
             *reinterpret_cast<float4*>(a.out + (int64_t)row * ncols + c0 + (lane & 7) * 4) = val;
-            s1.x += val.x; s1.y += val.y; s1.z += val.z; s1.w += val.w;
-            s2.x = fmaf(val.x, val.x, s2.x); s2.y = fmaf(val.y, val.y, s2.y);
-            s2.z = fmaf(val.z, val.z, s2.z); s2.w = fmaf(val.w, val.w, s2.w);
+            stat_add(s1, s2, val, pv);
           }
         }
         if (stats && part == nullptr) {                    // fold the 4 row groups (lane >> 3), lanes 0-7 keep the sums
@@ -764,7 +764,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(kColThreads)
 conv_os_fold_kernel(const int4* __restrict__ split_tiles, const int32_t* __restrict__ num,
                     const int32_t* __restrict__ out_row, const float* __restrict__ scratch, int ncols, int tile_rows,
-                    float* __restrict__ out, float* __restrict__ partials) {
+                    float* __restrict__ out, float* __restrict__ partials, const float* __restrict__ pivot) {
   pdl_enter();
   __shared__ float4 s_stage[STATS ? kColStageFloat4 : 1];
   __shared__ int s_rows[4 * kTileRows];
@@ -781,6 +781,7 @@ conv_os_fold_kernel(const int4* __restrict__ split_tiles, const int32_t* __restr
       s_rows[r] = __ldg(out_row + (int64_t)sp.x * tile_rows + slice0 + r);
     __syncthreads();
     const int ch = threadIdx.x * 4;
+    const float4 pv = STATS ? stat_pivot(pivot, ch) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float* p0 = scratch + (size_t)sp.z * tile_rows * ncols + ch;
     const size_t cstride = (size_t)tile_rows * ncols;
     constexpr int RB = 4;
@@ -806,10 +807,7 @@ conv_os_fold_kernel(const int4* __restrict__ split_tiles, const int32_t* __restr
         for (int c = 1; c < 4; ++c)
           if (c < sp.y) add4(acc, x[i][c]);
         *reinterpret_cast<float4*>(out + (int64_t)row * ncols + ch) = acc;
-        if (STATS) {
-          add4(s1, acc);
-          fma4(s2, acc, acc);
-        }
+        if (STATS) stat_add(s1, s2, acc, pv);
       }
     }
   }
@@ -959,6 +957,7 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
   a.partials = stats ? (float*)workspace : nullptr;
   a.scratch = workspace ? (float*)((char*)workspace + os_partials_bytes(ncols, scratch_slots)) : nullptr;
   a.valid_rows = valid_rows;
+  a.pivot = stats ? running_mean : nullptr;
   a.trace = (unsigned long long*)trace;
   a.n_out = n_out;
   a.unit_cap = (int)unit_cap; a.K = K; a.kflip = kflip; a.red = red; a.ncols = ncols;
@@ -1028,10 +1027,10 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
     float* fparts = stats ? a.partials + (size_t)grid * 2 * ncols : nullptr;
     if (stats)
       launch_pdl(conv_os_fold_kernel<true>, dim3(fgrid, kOsFoldSlices), dim3(cv, ry), 0, s, (const int4*)split_tiles, num,
-                 out_row, (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
+                 out_row, (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts, a.pivot);
     else
       launch_pdl(conv_os_fold_kernel<false>, dim3(fgrid, kOsFoldSlices), dim3(cv, ry), 0, s, (const int4*)split_tiles,
-                 num, out_row, (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts);
+                 num, out_row, (const float*)a.scratch, (int)ncols, (int)tile_rows, out, fparts, a.pivot);
     nparts += fgrid * kOsFoldSlices;
   }
   if (stats && !(a.dbg & 8))

@@ -465,10 +465,13 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
 template <bool STATS, int RB>
 __global__ void __launch_bounds__(kColThreads)
 conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos, int64_t n_rows, int kpad, int ncols,
-                   int rows_per_cta, float* __restrict__ out, float* __restrict__ partials) {
+                   int rows_per_cta, float* __restrict__ out, float* __restrict__ partials,
+                   const float* __restrict__ pivot, const int32_t* __restrict__ valid_rows) {
   pdl_enter();
   __shared__ float4 s_stage[STATS ? kColStageFloat4 : 1];
   const int ch = threadIdx.x * 4;
+  const float4 pv = STATS ? stat_pivot(pivot, ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t n_stat = STATS ? effective_rows(n_rows, valid_rows) : 0;    // padding rows stay out of the shifted sums
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row1 = row0 + rows_per_cta < n_rows ? row0 + rows_per_cta : n_rows;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
@@ -521,10 +524,7 @@ conv_reduce_kernel(const float* __restrict__ P, const int32_t* __restrict__ ppos
         }
       }
       *reinterpret_cast<float4*>(out + row * ncols + ch) = acc;
-      if (STATS) {
-        add4(s1, acc);
-        fma4(s2, acc, acc);
-      }
+      if (STATS && row < n_stat) stat_add(s1, s2, acc, pv);
     }
   }
   if (STATS) col_publish(s1, s2, partials, ncols, s_stage);
@@ -1010,19 +1010,19 @@ static int launch_reduce(const float* partial, const int32_t* ppos, int64_t n_ro
                  "%s: statistics need stat and a workspace of ft3d_bn_workspace(ncols) bytes", what);
     switch (row_batch()) {
       case 1: launch_pdl(conv_reduce_kernel<true, 1>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
-                                                        (float*)workspace); break;
+                                                        (float*)workspace, (const float*)running_mean, valid_rows); break;
       case 2: launch_pdl(conv_reduce_kernel<true, 2>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
-                                                        (float*)workspace); break;
+                                                        (float*)workspace, (const float*)running_mean, valid_rows); break;
       default: launch_pdl(conv_reduce_kernel<true, 4>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out,
-                                                        (float*)workspace); break;
+                                                        (float*)workspace, (const float*)running_mean, valid_rows); break;
     }
     launch_pdl(col_finalize_kernel<0>, dim3(ncols / 4), dim3(kColThreads), 0, s, (const float*)workspace, g.grid, ncols, n_rows, eps, momentum,
                                                              stat, running_mean, running_var, 0, valid_rows);
   } else {
     switch (row_batch()) {
-      case 1: launch_pdl(conv_reduce_kernel<false, 1>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr); break;
-      case 2: launch_pdl(conv_reduce_kernel<false, 2>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr); break;
-      default: launch_pdl(conv_reduce_kernel<false, 4>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr); break;
+      case 1: launch_pdl(conv_reduce_kernel<false, 1>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr, nullptr, nullptr); break;
+      case 2: launch_pdl(conv_reduce_kernel<false, 2>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr, nullptr, nullptr); break;
+      default: launch_pdl(conv_reduce_kernel<false, 4>, dim3(g.grid), dim3(g.block), 0, s, partial, ppos, n_rows, kpad, ncols, g.rows_per_cta, out, nullptr, nullptr, nullptr); break;
     }
   }
   return check_launch(what);

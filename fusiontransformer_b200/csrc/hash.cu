@@ -330,7 +330,7 @@ int ft3d_table_build(const int64_t* keys, int64_t n, uint64_t* table_keys, int32
                      int64_t cap, ft3d_stream_t stream) {
   FT3D_REQUIRE(table_keys && table_vals && cap >= 2 && (cap & (cap - 1)) == 0 && cap <= (1LL << 31),
                "ft3d_table_build: capacity must be a power of two <= 2^31");
-  FT3D_REQUIRE(n >= 0 && 2 * n <= cap || n < 512, "ft3d_table_build: capacity %lld too small for %lld keys",
+  FT3D_REQUIRE(n >= 0 && 2 * n <= cap, "ft3d_table_build: capacity %lld too small for %lld keys (need >= 2n)",
                (long long)cap, (long long)n);
   cudaStream_t s = (cudaStream_t)stream;
   table_init_kernel<<<grid_for(cap, 256), 256, 0, s>>>((unsigned long long*)table_keys, table_vals, cap);

@@ -327,7 +327,16 @@ class GraphedStep:
             ops.ROW_COUNTS = prev_counts
         return loss
 
-    LOADED = object()      # token: prepare() has already put the batch into the static buffers
+    class Loaded:
+        """Token returned by ``prepare``: the batch already sits in the static buffers.  ``inverse`` / ``kept`` are the
+        host-side maps of that batch (predictions of the unique voxels -> the original points, reference
+        ``data/utils/validate.py:10-11``; the bounds mask of the dataloader) -- exact-size tensors that never enter
+        the graph."""
+
+        def __init__(self, inverse=None, kept=None):
+            self.inverse, self.kept = inverse, kept
+
+    LOADED = Loaded()      # a token without maps (kept for callers that compare by identity)
 
     def prepare(self, batch, device="cuda"):
         """For plan.Prefetcher: upload + voxelize + build the exact geometry of ``batch`` and, when it fits the captured
@@ -340,12 +349,12 @@ class GraphedStep:
             if self.done is not None:
                 torch.cuda.current_stream().wait_event(self.done)
             self.static.load(plan)
-            return GraphedStep.LOADED
+            return GraphedStep.Loaded(plan.extras.get("inverse"), plan.extras.get("kept"))
         return plan
 
     def step(self, plan):
         """``plan``: a GeometryPlan, or the token returned by ``prepare``."""
-        if plan is not GraphedStep.LOADED:
+        if not isinstance(plan, GraphedStep.Loaded):
             if self.static is None or not self.static.fits(plan):
                 loss = self._capture(plan)
                 self._mark_done()

@@ -4,7 +4,8 @@
 reference's signatures, caches (``z.additional_features``, ``z.idx_query``, ``z.weights``) and results, but
 each map build is ONE libft3d launch against the per-stride coordinate table instead of the reference's
 hash -> table rebuild -> query -> count -> ~30 elementwise kernels.  The reference's own utils.py also runs
-unmodified on the operator-level API in ``functional`` (tests/test_gpu_glue.py checks both agree).
+unmodified on the operator-level API in ``functional`` (tests/test_reference_topology.py executes it on the oracle
+alias; tests/test_gpu_ops.py holds these fused versions to the oracle's results).
 """
 from __future__ import annotations
 

@@ -94,6 +94,10 @@ def test_error_convention_of_the_hot_path_entry_points():
     with pytest.raises(_lib.Ft3dError, match="output pitch"):
         L.bn_apply(p, 10, 64, p, p, p, None, 1, p, None, 32, None, None)            # pitch smaller than the row
     L.confusion_update(p, p, 0, 20, -100, None, p, None)
+    with pytest.raises(_lib.Ft3dError, match="too small"):                          # load factor <= 1/2, whatever n
+        L.table_build(p, 100, p, p, 128, None)
+    with pytest.raises(_lib.Ft3dError, match="power of two"):
+        L.table_build(p, 10, p, p, 100, None)
     assert int(L.seg_loss_workspace()) >= 3 * 1024 * 8 and int(L.bn_workspace(256)) > 0
 
 

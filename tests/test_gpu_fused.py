@@ -340,3 +340,45 @@ def test_deconv_cat_in_place_equals_cat(monkeypatch, small_batch, mode, tol):
     if a[1] is not None:                                                      # bf16 twin of the whole concatenation
         assert a[1].shape == a[0].shape and rel_l2(a[1], b[0].bfloat16().float()) < 1e-6
     assert rel_l2(a[2], b[2]) < 1e-4 and rel_l2(a[4], b[4]) < 1e-4 and rel_l2(a[5], b[5]) < 1e-4
+
+
+@pytest.mark.parametrize("producer", ["bn_stats", "conv_os", "conv_reduce"])
+def test_statistics_survive_a_large_mean(monkeypatch, voxels, producer):
+    """BatchNorm statistics are shifted sums around the running mean (csrc/bn_common.cuh): a channel whose mean is
+    1000x its standard deviation (mean 100, std 0.1) keeps its variance once the running mean has found the
+    neighbourhood -- raw fp32 E[y^2] - mean^2 returns noise there (nn.BatchNorm1d / cuDNN use Welford and do not)."""
+    import fusiontransformer_b200 as ft
+    from fusiontransformer_b200 import conv_engine, ops
+    g = torch.Generator().manual_seed(7)
+    C = voxels.C.int()
+    n, c = C.shape[0], 64
+    y = (100.0 + 0.1 * torch.randn(n, c, generator=g)).cuda()
+    if producer == "bn_stats":
+        run = lambda rm, rv: (ops.bn_stats(y, 1e-5, 0.1, rm, rv), y)
+    else:
+        # an identity-like convolution (only the centre offset carries weight) reproduces y, offset included
+        monkeypatch.setenv("FT3D_CONV_ALGO", "os" if producer == "conv_os" else "pairs")
+        km = ft.nn.functional.build_kernel_map(C.cuda(), C.cuda(), 3, 1)
+        w = torch.zeros(27, c, c)
+        w[13] = torch.eye(c)
+        w = w.cuda()
+        x16 = ops.to_bf16(y)
+        if producer == "conv_os":
+            def run(rm, rv):
+                out, stat = conv_engine.os_conv(x16, km, w, "forward", bn=(1e-5, 0.1, rm, rv))
+                return stat, out
+        else:
+            km.ppos
+
+            def run(rm, rv):
+                out, stat = ops.conv_reduce_bn(conv_engine.pairs_partial(x16, km, w, "forward")[0], km.ppos, c, 1e-5, 0.1,
+                                               rm, rv)
+                return stat, out
+    rm = torch.full((c,), 99.9, device="cuda")
+    rv = torch.ones(c, device="cuda")
+    stat, out = run(rm, rv)
+    mean, var = out.double().mean(0), out.double().var(0, unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    assert (stat[0].double() - mean).abs().max() < 1e-4
+    assert ((stat[1].double() - rstd) / rstd).abs().max() < 2e-3
+    assert (rm.double() - (0.9 * 99.9 + 0.1 * mean)).abs().max() < 1e-4

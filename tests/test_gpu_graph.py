@@ -139,3 +139,26 @@ def test_eval_between_replays_sees_the_updated_weights(monkeypatch):
         want = evaluate()
         # (the point->voxel scatter sums with fp32 atomics: equal up to summation order; a stale image differs by ~1e-2)
         assert ((got - want).norm() / want.norm()).item() < 1e-3
+
+
+def test_prepare_token_carries_the_point_maps(monkeypatch):
+    """``GraphedStep.prepare`` (the prefetch path) loads the batch into the static buffers and returns a token; the
+    token keeps the host-side maps of that batch -- ``inverse`` (unique voxel -> original points, reference
+    data/utils/validate.py:10-11) and ``kept`` -- so predictions of a replayed step can be mapped back to the points."""
+    from fusiontransformer_b200 import dataflow
+    from fusiontransformer_b200.graph import GraphedStep
+    monkeypatch.setenv("FT3D_CONV", "tc")
+    batches = _host_batches()
+    net, body = _trainer("tc", optimize=False)
+    gs = GraphedStep(body, modules=[net])
+    gs.step(dataflow.prepare_batch(batches[0], "cuda"))       # capture
+    for hb in batches[:2]:
+        ref = dataflow.prepare_batch(hb, "cuda")
+        tok = gs.prepare(hb, "cuda")
+        if not isinstance(tok, GraphedStep.Loaded):            # does not fit the captured capacities: a plan comes back
+            assert "inverse" in tok.extras
+            gs.step(tok)
+            continue
+        assert torch.equal(tok.inverse, ref.extras["inverse"]) and torch.equal(tok.kept, ref.extras["kept"])
+        loss = gs.step(tok)
+        assert torch.isfinite(loss).all()
