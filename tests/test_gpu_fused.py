@@ -338,7 +338,9 @@ def test_deconv_cat_in_place_equals_cat(monkeypatch, small_batch, mode, tol):
     a, b = outs
     assert rel_l2(a[0], b[0]) < 1e-6 and rel_l2(a[3], b[3]) < 1e-6            # same kernels, same rows
     if a[1] is not None:                                                      # bf16 twin of the whole concatenation
-        assert a[1].shape == a[0].shape and rel_l2(a[1], b[0].bfloat16().float()) < 1e-6
+        # (the second pass sees `down`'s updated running mean as the pivot of its shifted sums: rows agree to 1e-7,
+        # which may flip a handful of bf16 roundings)
+        assert a[1].shape == a[0].shape and rel_l2(a[1], b[0].bfloat16().float()) < 1e-5
     assert rel_l2(a[2], b[2]) < 1e-4 and rel_l2(a[4], b[4]) < 1e-4 and rel_l2(a[5], b[5]) < 1e-4
 
 
