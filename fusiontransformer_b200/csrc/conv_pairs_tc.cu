@@ -672,8 +672,6 @@ struct Wg2Header {
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   int32_t off[40];
-  int32_t pa[2][kTileRows];
-  int32_t pb[2][kTileRows];
 };
 
 __global__ void __launch_bounds__(kV3Threads)
@@ -750,39 +748,69 @@ conv_wgrad_pairs_tc_v2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
   } else
   if (warp < 4) {
     // ------------------------------------------------------------------ gather producers
-    UnitCursor uc;
-    uc.seek(hdr->off, K, T, u0);
-    for (int u = u0; u < u1; ++u, uc.next()) {
-      const int mb = uc.mb, begin = uc.c.begin, end = uc.c.end;
-      const int p = begin + tid;
-      int ia = -1, ib = -1;
-      if (p < end) {
-        if (pairs != nullptr) {
-          const int2 pr = __ldg(pairs + p);
-          ia = ca ? pr.y : pr.x;
-          ib = ca ? pr.x : pr.y;
-        } else {
-          ia = ib = p;
+    // Thread t owns 16-byte chunk c = t & 7 of the tile rows r_j = (t >> 3) + 16 j, j = 0..7, in EVERY block of a stage
+    // (8 lanes = one 128-byte row segment, as before).  The 8 pair entries of those rows are read straight from the
+    // pair list into registers -- requested one unit ahead, so the L2 round trip of the indices hides behind the
+    // previous unit's gathers -- and a block is 8 cp.async per thread: one 64-bit multiply-add and the copy.  (The
+    // first version staged the tile's indices in shared memory and walked a runtime-length loop: shared-memory load ->
+    // address -> copy, ~180 cycles per copy and thread, 11 B/cycle/SM -- ten times slower than the tensor pipe.)
+    const int c = tid & 7, r0 = tid >> 3;
+    const uint32_t dst_t = (uint32_t)(r0 * kBlockRowBytes) + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 j) & 7 == r0 & 7
+    auto load_rows = [&](const UnitCursor& cur, bool live, int (&ia)[8], int (&ib)[8]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int p = cur.c.begin + r0 + 16 * j;
+        ia[j] = ib[j] = -1;
+        if (live && p < cur.c.end) {
+          if (pairs != nullptr) {
+            const int2 pr = __ldg(pairs + p);
+            ia[j] = ca ? pr.y : pr.x;
+            ib[j] = ca ? pr.x : pr.y;
+          } else {
+            ia[j] = ib[j] = p;
+          }
         }
       }
-      const int it = u - u0, dbuf = it & 1;
-      hdr->pa[dbuf][tid] = ia;
-      hdr->pb[dbuf][tid] = ib;
-      named_bar_sync(1, kPProducers);
+    };
+    UnitCursor uc;
+    uc.seek(hdr->off, K, T, u0);
+    int ia[8], ib[8], na[8], nb[8];
+    load_rows(uc, true, ia, ib);
+    for (int u = u0; u < u1; ++u) {
+      const int mb = uc.mb;
+      uc.next();
+      load_rows(uc, u + 1 < u1, na, nb);                   // next unit's rows: in flight under this unit's gathers
+      const int it = u - u0;
       const int slot = it % nslots;
       const uint32_t use = (uint32_t)(it / nslots);
       if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
-      uint8_t* st = smem + (size_t)slot * stage_bytes;
+      const uint32_t st = smem_u32(smem + (size_t)slot * stage_bytes) + dst_t;
       const int m_valid = cin - mb * 128 < 128 ? cin - mb * 128 : 128;
       for (int blk = 0; blk * 64 < m_valid; ++blk) {
         const int width = m_valid - blk * 64 < 64 ? m_valid - blk * 64 : 64;
-        gather_block_bf16(st + blk * kBlockBytes, a, cin, mb * 128 + blk * 64, width >> 3, tid, hdr->pa[dbuf]);
+        if (c * 8 < width) {
+          const __nv_bfloat16* src = a + mb * 128 + blk * 64 + c * 8;
+          const uint32_t dst = st + (uint32_t)(blk * kBlockBytes);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            cp_async_16(dst + (uint32_t)(16 * j * kBlockRowBytes), src + (ia[j] >= 0 ? (int64_t)ia[j] * cin : 0),
+                        ia[j] >= 0 ? 16u : 0u);
+        }
       }
       for (int blk = 0; blk < nb_blocks; ++blk) {
         const int width = cout - blk * 64 < 64 ? cout - blk * 64 : 64;
-        gather_block_bf16(st + (a_blocks + blk) * kBlockBytes, b, cout, blk * 64, width >> 3, tid, hdr->pb[dbuf]);
+        if (c * 8 < width) {
+          const __nv_bfloat16* src = b + blk * 64 + c * 8;
+          const uint32_t dst = st + (uint32_t)((a_blocks + blk) * kBlockBytes);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            cp_async_16(dst + (uint32_t)(16 * j * kBlockRowBytes), src + (ib[j] >= 0 ? (int64_t)ib[j] * cout : 0),
+                        ib[j] >= 0 ? 16u : 0u);
+        }
       }
       cp_async_arrive_noinc(&hdr->full[slot]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ia[j] = na[j], ib[j] = nb[j];
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
