@@ -48,7 +48,6 @@ struct OsHeader {
   uint64_t acc_full[2], acc_empty[2];
   uint64_t pfull[kOsMaxSlots];                 // CTA pairs: rank 1's half of the stage has landed (remote arrive)
   uint32_t tmem_base;
-  int32_t idx[2][kTileRows];                   // LDGSTS mode: gather indices of the pass being issued
 };
 
 struct OsArgs {
@@ -448,6 +447,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
           rr[i][0] = __shfl_sync(0xffffffffu, r4.x, i); rr[i][1] = __shfl_sync(0xffffffffu, r4.y, i);
           rr[i][2] = __shfl_sync(0xffffffffu, r4.z, i); rr[i][3] = __shfl_sync(0xffffffffu, r4.w, i);
         }
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
           if (ring.round > 0) mbar_wait_a(empty0 + 8u * ring.slot, (ring.round & 1) ^ 1);
           if (DBG && fine != nullptr && tid == 0 && cnt < 512) fine[cnt * 4] = os_now();
@@ -497,6 +497,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
           ++queued;
         }
         const uint8_t* bsrc = a.wpacked + (size_t)k * nkb * b_bytes;
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb, bsrc += b_bytes) {
           if (ring.round > 0) mbar_wait_a(empty0 + 8u * ring.slot, (ring.round & 1) ^ 1);
           if (elect_one_sync()) {
@@ -520,32 +521,64 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
     }
   } else if (!TMA && warp < 4) {
     // ------------------------------------------------------------------ producers: 16-byte cp.async row pieces
+    // Thread t owns 16-byte chunk c = t & 7 of the tile rows r_j = (t >> 3) + 16 j, j = 0..7 (8 lanes = one 128-byte row
+    // segment).  Its 8 gather indices of a pass are read straight from the schedule into registers, kOsAhead passes
+    // ahead; a k-block is then 8 cp.async per thread -- one 64-bit multiply-add and the copy each.  (Staging the
+    // indices in shared memory and walking a runtime-length loop cost a dependent shared-memory load per copy.)
     OsPassIter it;
     it.init(a.units, U, first, step);
-    uint32_t cnt = 0, np = 0;
-    int g_n = it.valid() ? __ldg(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base + tid) : -1;
-    while (it.valid()) {
-      const int ib = (int)(np & 1);
-      hdr->idx[ib][tid] = g_n;
-      it.next();
-      ++np;
-      if (it.valid()) g_n = __ldg(a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base + tid);
-      os_named_bar_sync(1, kOsProducers);
-      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-        const int slot = (int)(cnt % (uint32_t)nslots);
-        const uint32_t use = cnt / (uint32_t)nslots;
-        if (use > 0) mbar_wait(&hdr->empty[slot], (use & 1) ^ 1);
-        const uint32_t base = smem_u32(smem + (size_t)slot * stage_bytes);
-        const int width = red - kb * 64 < 64 ? red - kb * 64 : 64;
-        const int nchunk = width >> 3;
-        for (int q = tid; q < kTileRows * 8; q += kOsProducers) {
-          const int r = q >> 3, c = q & 7;
-          const int g = hdr->idx[ib][r];
-          const bool live = g >= 0 && c < nchunk;
-          const __nv_bfloat16* p = a.in + (live ? (int64_t)g * red + kb * 64 + c * 8 : 0);
-          os_cp_async_16(base + r * kBlockRowBytes + ((c ^ (r & 7)) << 4), p, live ? 16u : 0u);
+    const int c = tid & 7, r0 = tid >> 3;
+    const uint32_t dst_t = (uint32_t)(r0 * kBlockRowBytes) + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 j) & 7 == r0 & 7
+    int rq[kOsAhead][8];
+    int queued = 0;
+#pragma unroll
+    for (int d = 0; d < kOsAhead; ++d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rq[d][j] = -1;
+      if (it.valid()) {
+        const int32_t* pi = a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base + r0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rq[d][j] = __ldg(pi + 16 * j);
+        it.next();
+        ++queued;
+      }
+    }
+    OsRing ring;
+    ring.init(nslots);
+    const __nv_bfloat16* src0 = a.in + c * 8;
+    uint32_t np = 0, cnt = 0;
+    while (queued > 0) {
+#pragma unroll
+      for (int d = 0; d < kOsAhead; ++d) {
+        if (queued == 0) break;
+        int g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = rq[d][j];
+        --queued;
+        if (DBG) ++np;
+        if (it.valid()) {
+          const int32_t* pi = a.pass_idx + (int64_t)it.pass() * a.tile_rows + row_base + r0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rq[d][j] = __ldg(pi + 16 * j);
+          it.next();
+          ++queued;
         }
-        os_cp_async_arrive_noinc(&hdr->full[slot]);
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (ring.round > 0) mbar_wait_a(empty0 + 8u * ring.slot, (ring.round & 1) ^ 1);
+          if (DBG && fine != nullptr && tid == 0 && cnt < 512) fine[cnt * 4] = os_now();
+          if (DBG) ++cnt;
+          if (c * 8 < red - kb * 64) {
+            const uint32_t dst = smem0 + ring.slot * (uint32_t)stage_bytes + dst_t;
+            const __nv_bfloat16* src = src0 + kb * 64;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              os_cp_async_16(dst + (uint32_t)(16 * j * kBlockRowBytes), src + (g[j] >= 0 ? (int64_t)g[j] * red : 0),
+                             g[j] >= 0 ? 16u : 0u);
+          }
+          os_cp_async_arrive_noinc(&hdr->full[ring.slot]);
+          ring.advance();
+        }
       }
     }
     if (DBG && tr != nullptr && tid == 0) tr[1] = os_now(), tr[5] = np;
@@ -558,6 +591,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
       for (; it.valid(); it.next()) {
         int k = __ldg(a.pass_k + it.pass());
         if (a.kflip) k = a.K - 1 - k;
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb, ++cnt) {
           const int slot = (int)(cnt % (uint32_t)nslots);
           const uint32_t use = cnt / (uint32_t)nslots;
@@ -576,9 +610,11 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         OsRing ring;
         ring.init(nslots);
         int np_n = first < U ? __ldg(a.units + 2 * (int64_t)first).y : 0;
+#pragma unroll 1
         for (int u = first; u < U; u += step) {
           const int np = np_n;
           if (u + step < U) np_n = __ldg(a.units + 2 * (int64_t)(u + step)).y;
+#pragma unroll 1
           for (int q = 0; q < np * nkb; ++q) {
             mbar_wait_a(full0 + 8u * ring.slot, ring.round & 1);
             mbar_arrive_remote(&hdr->pfull[ring.slot], 0);
@@ -604,6 +640,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
       ring.init(nslots);
       uint32_t cnt = 0, use_acc = 0;
       int np_n = first < U ? __ldg(a.units + 2 * (int64_t)first).y : 0;
+#pragma unroll 1
       for (int u = first; u < U; u += step) {
         const int np = np_n;
         if (u + step < U) np_n = __ldg(a.units + 2 * (int64_t)(u + step)).y;
@@ -617,7 +654,9 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * a.tcols);
         uint32_t acc = 0;                                              // the unit's first k-step overwrites
+#pragma unroll 1
         for (int q = 0; q < np; ++q) {
+#pragma unroll 1
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait_a(full0 + 8u * ring.slot, ring.round & 1);
             if (PAIR) mbar_wait_cluster_a(pfull0 + 8u * ring.slot, ring.round & 1);
@@ -667,6 +706,7 @@ conv_os_kernel(const __grid_constant__ CUtensorMap tmap, const OsArgs a) {
     uint32_t use_acc = 0, nunits = 0, nsplit_units = 0;
     int4 u0_n = make_int4(0, 0, 0, 1), u1_n = make_int4(0, 0, 0, 0);
     if (first < U) u0_n = __ldg(a.units + 2 * (int64_t)first), u1_n = __ldg(a.units + 2 * (int64_t)first + 1);
+#pragma unroll 1
     for (int u = first; u < U; u += step, ++nunits) {
       const int4 u0 = u0_n, u1 = u1_n;                     // {first pass, passes, tile, chunks}, {chunk, scratch base}
       if (u + step < U) u0_n = __ldg(a.units + 2 * (int64_t)(u + step)), u1_n = __ldg(a.units + 2 * (int64_t)(u + step) + 1);
@@ -853,9 +893,16 @@ static int make_row_tmap(CUtensorMap* tm, const void* base, int64_t n_rows, int 
   return FT3D_OK;
 }
 
-static int os_gather_mode() {      // 1 = TMA gather4 (default), 0 = LDGSTS; read per call (a getenv is ~50 ns)
+// 1 = TMA gather4, 0 = 16-byte cp.async (LDGSTS).  FT3D_OS_GATHER=tma|ldgsts forces one; by default the narrower layers
+// (red <= 192) take the cp.async path and the wide ones the TMA path: the TMA unit accepts one gathered row per ~7.5
+// cycles whatever its width (measured: a 128-row block every ~0.5 us, tools/conv_os_probe.py --fine), which bounds
+// the layers whose stages are small; 128 threads issuing 8 cp.async each from register-held indices are 10-25 %
+// faster there and equal on the 256-384-wide layers, whose stages are bounded by the weight blocks (read per call).
+static int os_gather_mode(int red, int cs) {
   const char* e = getenv("FT3D_OS_GATHER");
-  return (e != nullptr && (e[0] == 'l' || e[0] == 'L')) ? 0 : 1;
+  if (e != nullptr && (e[0] == 'l' || e[0] == 'L')) return 0;
+  if (e != nullptr && (e[0] == 't' || e[0] == 'T')) return 1;
+  return (cs > 1 || red > 192) ? 1 : 0;            // cluster schedules need the TMA path
 }
 
 static bool os_pair_mode() {       // 256-row tiles: cta_group::2 pairs (default) or, FT3D_OS_PAIR=0, two CTAs + B multicast
@@ -969,7 +1016,7 @@ int ft3d_conv_os(const void* in_bf16, int64_t n_in, const int32_t* units, const 
     const char* e = getenv("FT3D_OS_DEBUG");
     a.dbg = e ? atoi(e) : 0;
   }
-  const bool tma = os_gather_mode() == 1;
+  const bool tma = os_gather_mode(red, a.cs) == 1;
   const bool pair = tma && a.cs == 2 && os_pair_mode();      // 256-row tiles: one cta_group::2 MMA per CTA pair
   const int stage_bytes = tc::kBlockBytes + ncols * tc::kBlockRowBytes / (pair ? 2 : 1);
   const int fixed = 4 * kOsStageFloats * (int)sizeof(float) + 8 * ncols * (int)sizeof(float) + (int)sizeof(OsHeader) + 1024 + 64;

@@ -254,7 +254,6 @@ struct V3Header {
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   int32_t off[40];
-  int32_t idx[2][kTileRows];
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -316,32 +315,53 @@ conv_pairs_tc_v3_kernel(const __nv_bfloat16* __restrict__ in, const int2* __rest
   } else
   if (warp < 4) {
     // ------------------------------------------------------------------ gather producers
+    // Thread t owns 16-byte chunk c = t & 7 of the tile rows r_j = (t >> 3) + 16 j, j = 0..7; its 8 gather indices live
+    // in registers and are requested one tile ahead (see the wgrad kernel below: the shared-memory index staging of
+    // the first version cost a dependent shared-memory load per copy).
+    const int c = tid & 7, r0 = tid >> 3;
+    const uint32_t dst_t = (uint32_t)(r0 * kBlockRowBytes) + (uint32_t)((c ^ (r0 & 7)) << 4);
+    auto load_rows = [&](const TileCursor& tc_, bool live, int (&gi)[8]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int p = tc_.begin + r0 + 16 * j;
+        gi[j] = -1;
+        if (live && p < tc_.end) {
+          if (pairs != nullptr) {
+            const int2 pr = __ldg(pairs + p);
+            gi[j] = gather_col ? pr.y : pr.x;
+          } else {
+            gi[j] = p;
+          }
+        }
+      }
+    };
     uint32_t cnt = 0;
     TileCursor cur;
     cur.seek(hdr->off, K, g0);
-    for (int g = g0; g < g1; ++g, cur.next()) {
-      const int begin = cur.begin, end = cur.end;
-      const int p = begin + tid;
-      int gi = -1;
-      if (p < end) {
-        if (pairs != nullptr) {
-          const int2 pr = __ldg(pairs + p);
-          gi = gather_col ? pr.y : pr.x;
-        } else {
-          gi = p;
-        }
-      }
-      const int ib = (g - g0) & 1;
-      hdr->idx[ib][tid] = gi;
-      named_bar_sync(1, kPProducers);
+    int gi[8], gn[8];
+    load_rows(cur, true, gi);
+    const uint32_t ring0 = smem_u32(a_ring) + dst_t;
+    const __nv_bfloat16* src0 = in + c * 8;
+    for (int g = g0; g < g1; ++g) {
+      cur.next();
+      load_rows(cur, g + 1 < g1, gn);
+#pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         const int slot = (int)(cnt % (uint32_t)nslots);
         const uint32_t use = cnt / (uint32_t)nslots;
         if (use > 0) mbar_wait(&hdr->empty_a[slot], (use & 1) ^ 1);
-        const int width = red - kb * 64 < 64 ? red - kb * 64 : 64;
-        gather_block_bf16(a_ring + (size_t)slot * kBlockBytes, in, red, kb * 64, width >> 3, tid, hdr->idx[ib]);
+        if (c * 8 < red - kb * 64) {
+          const uint32_t dst = ring0 + (uint32_t)slot * (uint32_t)kBlockBytes;
+          const __nv_bfloat16* src = src0 + kb * 64;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            cp_async_16(dst + (uint32_t)(16 * j * kBlockRowBytes), src + (gi[j] >= 0 ? (int64_t)gi[j] * red : 0),
+                        gi[j] >= 0 ? 16u : 0u);
+        }
         cp_async_arrive_noinc(&hdr->full_a[slot]);
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gi[j] = gn[j];
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ weight loader
