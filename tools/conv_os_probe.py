@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--detail", action="store_true", help="per-CTA breakdown of the slowest CTAs")
     ap.add_argument("--fine", type=int, default=0, help="print the first N per-stage stamps of CTA 0")
     ap.add_argument("--only", default="", help="comma list of layer indices")
+    ap.add_argument("--modes", default="tma,ldgsts", help="gather modes to time (ncu captures: one mode)")
     ap.add_argument("--timeline-gather", default="tma", choices=["tma", "ldgsts"], help="gather mode of the traced launch")
     a = ap.parse_args()
     import fusiontransformer_b200 as ft
@@ -98,7 +99,7 @@ def main():
         for mode in ("tma", "ldgsts"):
             os.environ["FT3D_OS_GATHER"] = mode
             t[mode] = (graph_time(lambda: conv_engine.os_conv(x16, km, w, "forward", bn=bn))
-                       if (mode == "tma" or a.cluster == 1) else float("nan"))
+                       if ((mode == "tma" or a.cluster == 1) and mode in a.modes.split(",")) else float("nan"))
         os.environ["FT3D_OS_GATHER"] = a.timeline_gather
         km.ppos
         tp = graph_time(lambda: ops.conv_reduce_bn(conv_engine.pairs_partial(x16, km, w, "forward")[0], km.ppos, cout,
