@@ -8,6 +8,8 @@ One "step" = one data-parallel training step of the middle-fusion 3D branch on a
 `value`  : scans/s with the raw scans already resident in HBM.
 `e2e`    : the same through the public API with the batch in pinned HOST memory (H2D inside the timed region)
            and the loss read back every step.
+Default workload: configs[1] (nuScenes-shaped) at every N; the line also carries `configs2_kitti` = configs[2]
+(KITTI-shaped, BASELINE.json's data-parallel config) measured at the same N by a child run of this file.
 `--impl reference` times the CPU oracle (the reference's algorithm restated on PyTorch-CPU; torchsparse v1.1.0 is
 not installable offline) on the box's host cores, one scan per step.
 """
@@ -152,6 +154,37 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def run_configs2_child(args, rank, world):
+    """`bench.py --workload kitti` at the same N as a child of every rank (own rendezvous port); rank 0 returns the
+    child's line condensed, the other ranks None.  A failure is reported in the key, never raised."""
+    env = dict(os.environ)
+    if world > 1:
+        # torchrun's agent serves the parent's rendezvous store; the children make their own on a derived port
+        env.pop("TORCHELASTIC_USE_AGENT_STORE", None)
+        env["MASTER_ADDR"] = env.get("MASTER_ADDR", "127.0.0.1")
+        base = int(env.get("MASTER_PORT", "29500"))
+        env["MASTER_PORT"] = str(base + 1 if base < 65000 else base - 1)
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--workload", "kitti",
+           "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline", "--no-roofline",
+           "--fusion", args.fusion, "--fmap-format", args.fmap_format]
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        if rank != 0:
+            return None
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                return {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"],
+                        "ms_per_step": d["ms_per_step"], "e2e": d["e2e"], "n_gpus": d["n_gpus"],
+                        "scans_per_gpu": d["config"]["scans_per_gpu"], "parallelism": d["config"]["parallelism"],
+                        "cuda_graph": d["config"]["cuda_graph"], "clocks": d.get("clocks"),
+                        "note": "same bench.py, same N, --workload kitti, run in a child process before this line's "
+                                "own measurement: BASELINE.json configs[2], the data-parallel config"}
+        return {"error": "rc %d: %s" % (r.returncode, (r.stderr or "")[-300:])}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:300]} if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,8 +200,8 @@ def main():
                     help="memory format of the synthetic image-feature map the lift gathers from")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-baseline", action="store_true",
-                    help="at --gpus 1 with the default workload, skip the extra 1-GPU run of configs[2] (the workload "
-                         "every --gpus N > 1 run uses) that is reported as `scaling_baseline`")
+                    help="with the default workload, skip the extra run of configs[2] (KITTI-shaped) at the same N that "
+                         "is reported as `configs2_kitti`")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--prefetch-thread", dest="no_prefetch_thread", action="store_false",
                     help="build the next batch's geometry from a worker thread (GIL-bound: slower)")
@@ -186,7 +219,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     default_workload = args.workload is None
     if args.workload is None:
-        args.workload = "nuscenes" if args.gpus <= 1 else "kitti"
+        args.workload = "nuscenes"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -194,6 +227,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+
+    # configs[2] (KITTI-shaped, the data-parallel config of BASELINE.json) at the SAME N, in a child process per rank,
+    # before this process touches the GPU: every default line then carries both workloads -- `value` is configs[1] at
+    # every N (one workload along the whole 1/2/4/8 curve), `configs2_kitti` is configs[2] at that N.
+    configs2 = None
+    if default_workload and not args.no_scaling_baseline:
+        configs2 = run_configs2_child(args, rank, world)
 
     import torch.distributed as dist
     import fusiontransformer_b200 as ft
@@ -534,25 +574,6 @@ def main():
         for ms_, cnt, key in rows[:args.trace_top]:
             print("  %8.3f ms %6.1f x %7.1f us  %s" % (ms_, cnt, 1e3 * ms_ / max(cnt, 1e-9), key[:110]), file=sys.stderr)
 
-    # The data-parallel runs (--gpus 2/4/8) use configs[2] (KITTI-shaped); their single-GPU point is measured here, in
-    # a child process, so that the N = 1 line carries both the headline (configs[1]) and the scaling baseline.
-    scaling_baseline = None
-    if rank == 0 and world == 1 and default_workload and args.impl == "ours" and not args.no_scaling_baseline:
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--gpus", "1", "--workload", "kitti",
-                                "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-cpu-baseline",
-                                "--no-roofline", "--fusion", args.fusion, "--fmap-format", args.fmap_format],
-                               capture_output=True, text=True, timeout=600)
-            for ln in r.stdout.splitlines():
-                if ln.startswith("{"):
-                    d = json.loads(ln)
-                    scaling_baseline = {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"],
-                                        "ms_per_step": d["ms_per_step"], "e2e": d["e2e"], "n_gpus": 1,
-                                        "note": "same bench.py, --workload kitti --gpus 1: the single-GPU point of the "
-                                                "configs[2] scaling curve that --gpus 2/4/8 report"}
-        except Exception as e:  # noqa: BLE001
-            scaling_baseline = {"error": str(e)[:200]}
-
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sps, spstep, done = time_oracle(wl["shape"], steps=24, warmup=1, budget_s=15.0)
@@ -584,7 +605,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "scans/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernel_ms_per_step": shares, "scaling_baseline": scaling_baseline,
+            "kernel_ms_per_step": shares, "configs2_kitti": configs2,
         }
         print(json.dumps(line), flush=True)
     if pre is not None:
