@@ -213,9 +213,6 @@ def main():
     ap.add_argument("--trace-top", type=int, default=60)
     ap.add_argument("--trace-dump", default="", help="CSV of the last traced step, one row per GPU launch")
     ap.add_argument("--diag", action="store_true", help="print host-side enqueue time per phase (stderr)")
-    ap.add_argument("--prefetch-depth", type=int, default=1, choices=[1, 2, 3],
-                    help="geometry plans built ahead concurrently (plan.PrefetchQueue); 1 = one plan, built by "
-                         "GraphedStep.prepare straight into the graph's static buffers")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="build each batch's geometry inside its own step (host reads stall the launch queue)")
     args = ap.parse_args()
@@ -284,14 +281,8 @@ def main():
     # The geometry of batch i+1 (upload, voxelization, kernel maps: every host read of a data-dependent size) is
     # built on a high-priority side stream while batch i's convolutions run (fusiontransformer_b200/plan.py).
     from fusiontransformer_b200.plan import Prefetcher
-    prio = int(os.environ.get("FT3D_PREFETCH_PRIORITY", "-2"))
-    if not args.prefetch:
-        pre = None
-    elif args.prefetch_depth > 1:          # several plans in flight, each on its own thread + stream (plan.PrefetchQueue)
-        from fusiontransformer_b200.plan import PrefetchQueue
-        pre = PrefetchQueue(dev, depth=args.prefetch_depth, priority=prio)
-    else:
-        pre = Prefetcher(dev, threaded=not args.no_prefetch_thread, priority=prio)
+    pre = Prefetcher(dev, threaded=not args.no_prefetch_thread,
+                     priority=int(os.environ.get("FT3D_PREFETCH_PRIORITY", "-2"))) if args.prefetch else None
 
     diag = {} if args.diag else None
 
@@ -350,12 +341,7 @@ def main():
     cached_plans = {}
     prepare = gstep.prepare if gstep is not None else dataflow.prepare_batch
 
-    def prep_fn(eager):
-        # depth 1: the worker also copies the plan into the graph's static buffers (GraphedStep.prepare); deeper queues
-        # hand over exact-size plans and GraphedStep.step loads them on the compute stream, in step order
-        return dataflow.prepare_batch if (eager or args.prefetch_depth > 1) else prepare
-
-    def train_step(batch, nxt=None, eager=False, nxt2=None):
+    def train_step(batch, nxt=None, eager=False):
         t = time.perf_counter()
         if args.reuse_plans:          # diagnostic: geometry of each distinct batch built once (not a valid bench mode)
             plan = cached_plans.get(id(batch))
@@ -366,7 +352,7 @@ def main():
             plan = dataflow.prepare_batch(batch, dev)
         else:
             if pre._pending is None:
-                pre.submit(prep_fn(eager), batch, dev)
+                pre.submit(dataflow.prepare_batch if eager else prepare, batch, dev)
             plan = pre.get()
         t = tick("get_plan", t)
         if gstep is not None and not eager:
@@ -379,10 +365,7 @@ def main():
             opt.step()
             t = tick("optimizer", t)
         if pre is not None and nxt is not None:
-            if args.prefetch_depth > 1:
-                pre.top_up(prep_fn(eager), [nxt, nxt2], dev)
-            else:
-                pre.submit(prep_fn(eager), nxt, dev)
+            pre.submit(dataflow.prepare_batch if eager else prepare, nxt, dev)
         tick("prefetch_next", t)
         return loss
 
@@ -415,9 +398,8 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     L.calls.clear()
     replays0 = gstep.replays if gstep is not None else 0
-    ms = timed(lambda i: train_step(resident[i % nbatches], resident[(i + 1) % nbatches],
-                                    nxt2=resident[(i + 2) % nbatches]), args.steps)
-    while pre is not None and pre._pending is not None:
+    ms = timed(lambda i: train_step(resident[i % nbatches], resident[(i + 1) % nbatches]), args.steps)
+    if pre is not None and pre._pending is not None:
         pre.get()
     launches = _lib.launch_count(L.calls)
     if gstep is not None:
@@ -432,13 +414,12 @@ def main():
 
     # ---- end-to-end timing through the public API: pinned host batch -> H2D -> step -> loss to host
     def e2e_step(i):
-        loss = train_step(host[i % nbatches], host[(i + 1) % nbatches],     # pinned host batches: H2D inside the step
-                          nxt2=host[(i + 2) % nbatches])
+        loss = train_step(host[i % nbatches], host[(i + 1) % nbatches])     # pinned host batches: H2D inside the step
         return loss.item()
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
-    while pre is not None and pre._pending is not None:
+    if pre is not None and pre._pending is not None:
         pre.get()
     # sampled across BOTH timed regions (device-resident and end-to-end; 100 ms period): a 20-step region lasts ~0.13 s
     clocks = sampler.stop() if sampler else None
@@ -539,7 +520,7 @@ def main():
                 train_step(resident[i % nbatches], resident[(i + 1) % nbatches])
             torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) / args.trace * 1e3
-        while pre is not None and pre._pending is not None:
+        if pre is not None and pre._pending is not None:
             pre.get()
         tf = tempfile.NamedTemporaryFile(suffix=".json", delete=False).name
         prof.export_chrome_trace(tf)
@@ -611,7 +592,6 @@ def main():
                        "image_hw": [H, W], "feature_map_format": args.fmap_format,
                        "parallelism": "dp%d" % world, "optimizer": "Adam(lr 1e-4, wd 5e-4)",
                        "geometry_prefetch": bool(args.prefetch) and not args.reuse_plans,
-                       "prefetch_depth": args.prefetch_depth if args.prefetch else 0,
                        **({"INVALID_diagnostic": "geometry cached across steps"} if args.reuse_plans else {}),
                        "cuda_graph": ("whole step%s, %d capture(s)" % (
                            "" if world == 1 else (" incl. NCCL exchange" if in_graph else ", exchange after replay"),

@@ -23,7 +23,7 @@ from . import conv_engine, ops
 from .functional import KernelMap, build_kernel_map, spdownsample
 from .ops import CoordTable
 
-__all__ = ["GeometryPlan", "build_plan", "Prefetcher", "PrefetchQueue"]
+__all__ = ["GeometryPlan", "build_plan", "Prefetcher"]
 
 
 @dataclass
@@ -188,43 +188,3 @@ class Prefetcher:
         if self._threaded and self._worker.is_alive():
             self._jobs.put(None)
             self._worker.join(timeout=5)
-
-
-class PrefetchQueue:
-    """``depth`` Prefetchers (each with its own worker thread and side stream) used round-robin: the plans of the next
-    ``depth`` batches are built concurrently.  One plan costs ~6 ms of wall time on its thread (≈150 entry-point calls
-    and ~15 host reads of data-dependent sizes, most of it spent waiting with the GIL released), about as long as the
-    step it is built under -- with one plan in flight the step rate is bounded by that thread, with two it is not.
-    Plans are consumed in submission order.  Same interface as ``Prefetcher`` (``submit`` / ``get`` / ``_pending`` /
-    ``close``) plus ``top_up``."""
-
-    def __init__(self, device=None, depth: int = 2, priority: int = -1):
-        from collections import deque
-        self.depth = depth
-        self._workers = [Prefetcher(device, threaded=True, priority=priority) for _ in range(depth)]
-        self._q = deque()
-        self._next = 0
-
-    @property
-    def _pending(self):
-        return "queued" if self._q else None
-
-    def submit(self, fn, *args):
-        assert len(self._q) < self.depth, "every worker already holds a batch"
-        w = self._workers[self._next]
-        self._next = (self._next + 1) % self.depth
-        w.submit(fn, *args)
-        self._q.append(w)
-
-    def top_up(self, fn, batches, *args):
-        """``batches``: the next batches in consumption order; those beyond what is already queued are submitted."""
-        want = [b for b in batches if b is not None][:self.depth]
-        for b in want[len(self._q):]:
-            self.submit(fn, b, *args)
-
-    def get(self):
-        return self._q.popleft().get()
-
-    def close(self):
-        for w in self._workers:
-            w.close()

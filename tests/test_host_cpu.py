@@ -104,43 +104,3 @@ def test_synthetic_scans_follow_the_survey_shapes_and_are_deterministic():
         assert not np.array_equal(a["points"], c["points"])
         if shape == "kitti":
             assert a["points"][:, 0].min() > 0                             # front camera: x > 0
-
-
-def test_prefetch_queue_order_and_top_up(monkeypatch):
-    """plan.PrefetchQueue: round-robin workers, FIFO consumption, top_up submits only what is not queued yet."""
-    from fusiontransformer_b200 import plan as plan_mod
-
-    class FakeWorker:
-        made = []
-
-        def __init__(self, device=None, threaded=False, priority=-1):
-            assert threaded
-            self.job = None
-            FakeWorker.made.append(self)
-
-        def submit(self, fn, *args):
-            assert self.job is None, "worker reused before its plan was consumed"
-            self.job = (fn, args)
-
-        def get(self):
-            fn, args = self.job
-            self.job = None
-            return fn(*args)
-
-        def close(self):
-            self.closed = True
-
-    monkeypatch.setattr(plan_mod, "Prefetcher", FakeWorker)
-    q = plan_mod.PrefetchQueue(device="cpu", depth=2)
-    assert q._pending is None and len(FakeWorker.made) == 2
-    f = lambda b, dev: (b, dev)  # noqa: E731
-    q.top_up(f, ["b1", "b2"], "dev")
-    assert q._pending is not None
-    assert q.get() == ("b1", "dev")
-    q.top_up(f, ["b2", "b3"], "dev")              # b2 is already queued: only b3 is submitted
-    assert q.get() == ("b2", "dev") and q.get() == ("b3", "dev") and q._pending is None
-    q.top_up(f, ["b4", None], "dev")              # a missing look-ahead batch is skipped
-    q.top_up(f, ["b4", "b5", "b6"], "dev")        # never more than `depth` in flight
-    assert [q.get(), q.get()] == [("b4", "dev"), ("b5", "dev")] and q._pending is None
-    q.close()
-    assert all(w.closed for w in FakeWorker.made)
